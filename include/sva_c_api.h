@@ -1,0 +1,159 @@
+/*
+ * sva_c_api.h — C ABI of libsva_b200.so: the B200 (sm_100a) implementation of the
+ * StereoVisionArray multi-camera depth hot path.
+ *
+ * Every entry point is `extern "C"`, takes plain pointers + sizes, returns an int status
+ * (0 = SVA_OK, negative = sva_status) and never retains a caller pointer after it returns.
+ * The reference has no error codes (failures are cv::Exception / UB); the adapter
+ * in include/sva_reference_api.hpp turns a non-zero status back into an exception.
+ *
+ * Citations `file:line` are into the reference tree (Nahuel-M/StereoVisionArray).
+ * Images are 8-bit, single channel, row-major: (data, rows, cols, step_bytes) == cv::Mat
+ * {data, rows, cols, step}.
+ */
+#ifndef SVA_C_API_H
+#define SVA_C_API_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SVA_API_VERSION 1
+#define SVA_MAX_PAIRS 32
+#define SVA_COST_CAP_MAX 4095      /* PACK_U16 costs live in [0, cap], cap <= 4095 */
+#define SVA_COST_INVALID_U32 0xFFFFFFFFu
+#define SVA_DISP_INVALID 0xFFFFu   /* u16 disparity of a rejected / masked / border pixel */
+#define SVA_SUBPIX_INVALID (-1.0f)
+
+typedef enum sva_status {
+    SVA_OK = 0,
+    SVA_ERR_BAD_ARG = -1,      /* null pointer, non-positive size, unsupported parameter */
+    SVA_ERR_ROI = -2,          /* a window leaves the image: the reference would throw cv::Exception (Mat::operator()(Rect)) */
+    SVA_ERR_CUDA = -3,         /* CUDA runtime error; text in sva_last_error() */
+    SVA_ERR_NO_DEVICE = -4,    /* no sm_100 device: there is NO CPU fallback */
+    SVA_ERR_STATE = -5,        /* stage called before the stage that produces its input */
+    SVA_ERR_NOMEM = -6
+} sva_status;
+
+/* enum pairType — include/functions.h:8-19, same values in the same order. */
+typedef enum sva_pair_type {
+    SVA_ORTHOGONAL = 0, SVA_DIAGONAL = 1, SVA_TO_CENTER = 2, SVA_LINE_HORIZONTAL = 3, SVA_LINE_VERTICAL = 4,
+    SVA_CROSS = 5, SVA_JUMP_CROSS = 6, SVA_TO_CENTER_SMALL = 7, SVA_MID_LEFT = 8, SVA_MID_TOP = 9
+} sva_pair_type;
+
+/* class Camera — include/Camera.h:6-21: data members in declaration order pos3D, f, pixel_size. */
+typedef struct sva_camera {
+    double pos[3];
+    double f;
+    double pixel_size;
+} sva_camera;
+
+typedef struct sva_image_u8 {
+    const uint8_t* data;
+    int32_t rows, cols;
+    size_t step; /* bytes between rows */
+} sva_image_u8;
+
+/* Parameters of the rectified-array ("volume") formulation; frozen spec in DESIGN.md §3. */
+typedef struct sva_params {
+    int32_t width, height;
+    int32_t num_disp;               /* D; multiple of 8, 8..256 */
+    int32_t min_disp;               /* disparity of volume index 0 (delta = min_disp + d) */
+    int32_t win_half;               /* k: SAD window is [x-k, x+k) x [y-k, y+k) — src/CameraStereoVision.cpp:44,57,77 */
+    int32_t n_pairs;                /* 1..SVA_MAX_PAIRS */
+    int32_t pair_gx[SVA_MAX_PAIRS]; /* grid offset of the other camera from the reference camera, in baselines */
+    int32_t pair_gy[SVA_MAX_PAIRS]; /* match of ref (x,y) at disparity delta is other (x - gx*delta, y - gy*delta) */
+    int32_t cost_shift;             /* PACK_U16: C = min(cost_cap, raw >> cost_shift), applied after the cross-pair sum */
+    int32_t cost_cap;               /* 1..SVA_COST_CAP_MAX; also the value of an invalid cell */
+    int32_t p1, p2;                 /* SGM penalties, 0 <= p1 <= p2 <= 4095 */
+    int32_t n_paths;                /* 0 (no aggregation: WTA on C), 4 or 8 */
+    int32_t lr_gx;                  /* 0 = no left-right check; -1/+1 = side of the virtual horizontal other view */
+    int32_t lr_max_diff;            /* reject when |d - d_other| > lr_max_diff */
+    int32_t subpixel;               /* 0/1: parabolic refinement of the integer winner */
+    int32_t reserved[8];
+} sva_params;
+
+typedef struct sva_ctx sva_ctx;
+
+/* ---- context ----------------------------------------------------------------------------------------------- */
+int sva_create(int device, sva_ctx** out);          /* one ctx per GPU; owns a stream and the HBM workspaces */
+int sva_destroy(sva_ctx* ctx);
+const char* sva_last_error(const sva_ctx* ctx);      /* valid until the next call on ctx */
+int sva_api_version(void);
+int sva_set_stream(sva_ctx* ctx, void* cuda_stream); /* run on a caller stream (e.g. torch's) instead of the ctx's own */
+int sva_synchronize(sva_ctx* ctx);
+int sva_kernel_launches(const sva_ctx* ctx, uint64_t* out_count); /* kernels launched by this ctx so far */
+
+/* ---- 1:1 shims of the reference's scalar helpers (host side, no GPU work) ------------------------------------ */
+/* Camera::project — src/Camera.cpp:15-22 */
+int sva_camera_project(const sva_camera* cam, const double pos3d[3], int32_t out_px[2]);
+/* Camera::inv_project — src/Camera.cpp:25-33 */
+int sva_camera_inv_project(const sva_camera* cam, const int32_t px[2], double out_ray[3]);
+/* bresenham — include/functions.h:45, src/functions.cpp:253-321.  Returns the number of points (may exceed cap; only cap are written). */
+int sva_bresenham(int32_t ax, int32_t ay, int32_t bx, int32_t by, int32_t* out_xy, int32_t cap);
+/* getCameraPairs — include/functions.h:34-36, src/functions.cpp:148-213.  camera_num < 0 = the 2-argument overload. */
+int sva_get_camera_pairs(int32_t n_cameras, int32_t pair_type, int32_t camera_num, int32_t* out_pairs, int32_t cap);
+/* Generalisation to an arbitrary rows x cols grid: pairs {ref, i} for every i != ref (TO_CENTER) or the
+ * 8-neighbourhood (TO_CENTER_SMALL), plus the grid offsets (gx, gy) = (col_i - col_ref, row_i - row_ref). */
+int sva_grid_pairs(int32_t grid_rows, int32_t grid_cols, int32_t ref_index, int32_t pair_type, int32_t* out_pairs,
+                   int32_t* out_gx, int32_t* out_gy, int32_t cap);
+
+/* ---- batched hot path, host buffers in / host buffers out (copies are inside the call) ----------------------- */
+/* getAbsDiff — include/functions.h:38, src/functions.cpp:215-218: exact sum |a-b| of two equal-size u8 ROIs. */
+int sva_abs_diff_u8(sva_ctx* ctx, const sva_image_u8* a, const sva_image_u8* b, double* out_sum);
+
+/* The reference driver's loop nest — src/CameraStereoVision.cpp:49-95 — as ONE call ("literal mode").
+ * images[n_images], cams[n_images]; pairs[2*n_pairs] = {ref, other}; mask may be NULL (= all ones).
+ * out_disp: rows x cols u8, zero where the reference leaves the Mat unwritten. */
+int sva_match_literal(sva_ctx* ctx, const sva_image_u8* images, const sva_camera* cams, int32_t n_images, const int32_t* pairs,
+                      int32_t n_pairs, const sva_image_u8* mask, int32_t win_half, double ray_near, double ray_far, uint8_t* out_disp);
+
+/* shiftPerspectiveWithDisparity — include/functions.h:26, src/functions.cpp:55-77 (gather remap, zero where unwritten). */
+int sva_shift_perspective_with_disparity(sva_ctx* ctx, const sva_camera* input_cam, const sva_camera* output_cam,
+                                         const sva_image_u8* disparity, const sva_image_u8* image, uint8_t* out);
+
+/* improveWithDisparity — include/functions.h:22, src/functions.cpp:11-52.  cams[2*n] = {cam0, cam1} per other image.
+ * Returns SVA_ERR_ROI where the reference would throw (a masked pixel whose 2k x 2k windows leave the image). */
+int sva_improve_with_disparity(sva_ctx* ctx, const sva_image_u8* disparity, const sva_image_u8* center, const sva_image_u8* images,
+                               const sva_camera* cams, int32_t n, const sva_image_u8* mask, int32_t window_size, uint8_t* out);
+
+/* depth = baseline * f / (disparity * pixel_size) in f64 — src/CameraStereoVision.cpp:47,98-100 (inf where disparity == 0). */
+int sva_disparity_to_depth(sva_ctx* ctx, const sva_image_u8* disparity, double baseline, double f, double pixel_size, double* out_depth);
+
+/* The whole volume-mode pipeline (cost volume -> SGM -> WTA/LR/sub-pixel), DESIGN.md §3.
+ * others[n_pairs] are the other views in pair order.  out_disp: u16 (min_disp + d, SVA_DISP_INVALID when rejected);
+ * out_subpix (may be NULL): f32. */
+int sva_depth_from_array(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others,
+                         const sva_image_u8* mask, uint16_t* out_disp, float* out_subpix);
+
+/* ---- staged, device-resident form of the same pipeline (what bench.py times with inputs already in HBM) ------- */
+typedef enum sva_stage {
+    SVA_STAGE_AD = 1,        /* K1a: A(y,x,d) = sum_k |R - I_k(shifted)|            -> u16 [H][W][D] */
+    SVA_STAGE_BOX = 2,       /* K1b: 2k x 2k box sum + shift/cap + validity          -> u16 [H][W][D] (C) */
+    SVA_STAGE_SGM = 3,       /* K2 (+ fused K3 in its last pass): S and the outputs  -> u16 [H][W][D], disparity maps */
+    SVA_STAGE_ALL = 100
+} sva_stage;
+
+int sva_frame_upload(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask);
+/* pair subset [pair_begin, pair_end) for SVA_STAGE_AD (pair sharding); pass 0, n_pairs for everything. */
+int sva_frame_set_pair_range(sva_ctx* ctx, int32_t pair_begin, int32_t pair_end);
+int sva_frame_run(sva_ctx* ctx, int32_t stage);
+/* CUDA-event time of `iters` back-to-back runs of `stage` on the ctx stream, in milliseconds (total, not mean). */
+int sva_frame_time(sva_ctx* ctx, int32_t stage, int32_t iters, float* out_ms);
+/* Per-kernel CUDA-event times of the last SVA_STAGE_* run: names[i] (static strings) / ms[i]; returns the count. */
+int sva_frame_kernel_times(sva_ctx* ctx, const char** names, float* ms, int32_t cap);
+int sva_frame_download_ad(sva_ctx* ctx, uint16_t* out);         /* [H][W][D] */
+int sva_frame_download_cost(sva_ctx* ctx, uint16_t* out);       /* [H][W][D] */
+int sva_frame_download_raw_cost(sva_ctx* ctx, uint32_t* out);   /* RAW_U32 recomputed from A: [H][W][D] */
+int sva_frame_download_sgm(sva_ctx* ctx, uint16_t* out);        /* S [H][W][D] (sum of the first n_paths-1 paths) */
+int sva_frame_download_disparity(sva_ctx* ctx, uint16_t* out_disp, float* out_subpix);
+/* Device pointer + byte size of the A volume, so a caller can reduce it across GPUs (NCCL via torch.distributed). */
+int sva_frame_ad_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SVA_C_API_H */
