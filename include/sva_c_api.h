@@ -143,8 +143,19 @@ int sva_frame_set_pair_range(sva_ctx* ctx, int32_t pair_begin, int32_t pair_end)
 int sva_frame_run(sva_ctx* ctx, int32_t stage);
 /* CUDA-event time of `iters` back-to-back runs of `stage` on the ctx stream, in milliseconds (total, not mean). */
 int sva_frame_time(sva_ctx* ctx, int32_t stage, int32_t iters, float* out_ms);
-/* Per-kernel CUDA-event times of the last SVA_STAGE_* run: names[i] (static strings) / ms[i]; returns the count. */
-int sva_frame_kernel_times(sva_ctx* ctx, const char** names, float* ms, int32_t cap);
+/* Runs `stage` once with a CUDA-event pair around every kernel: names[i] (static strings) / ms[i]; returns the kernel count. */
+int sva_frame_kernel_times(sva_ctx* ctx, int32_t stage, const char** names, float* ms, int32_t cap);
+/* sva_frame_time with an event pair around every kernel: per distinct kernel name, the summed time and the launch count. */
+int sva_frame_time_detailed(sva_ctx* ctx, int32_t stage, int32_t iters, float* out_total_ms, const char** names, float* sum_ms,
+                            int32_t* counts, int32_t cap);
+/* CUDA-event stopwatch on the ctx stream: times a sequence of host-buffer calls (the end-to-end path) on the device clock. */
+int sva_timer_start(sva_ctx* ctx);
+int sva_timer_stop(sva_ctx* ctx, float* out_ms);
+/* Test hooks: store_full_s != 0 makes the last SGM pass also write S_total; sgm_dir_mask != 0 runs exactly those path
+ * directions (bit i = direction i of {v+, v-, h+, h-, d++, d-+, d+-, d--}) as accumulate passes and skips the final pass. */
+int sva_frame_set_debug(sva_ctx* ctx, int32_t store_full_s, uint32_t sgm_dir_mask);
+/* After an external (cross-GPU) reduction has written the complete A volume into sva_frame_ad_device_ptr()'s buffer. */
+int sva_frame_mark_ad_ready(sva_ctx* ctx);
 int sva_frame_download_ad(sva_ctx* ctx, uint16_t* out);         /* [H][W][D] */
 int sva_frame_download_cost(sva_ctx* ctx, uint16_t* out);       /* [H][W][D] */
 int sva_frame_download_raw_cost(sva_ctx* ctx, uint32_t* out);   /* RAW_U32 recomputed from A: [H][W][D] */

@@ -1,0 +1,56 @@
+"""Loads stereovisionarray_b200/libsva_b200.so (the sm_100a CUDA library behind include/sva_c_api.h).
+
+There is NO CPU fallback: a missing library raises, and sva_create() fails on a machine without a B200-class GPU."""
+import ctypes as C
+import os
+
+from . import abi
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libsva_b200.so")
+
+# every symbol include/sva_c_api.h declares (checked by tests/test_abi.py against the header text)
+EXPORTS = [
+    "sva_create", "sva_destroy", "sva_last_error", "sva_api_version", "sva_set_stream", "sva_synchronize", "sva_kernel_launches",
+    "sva_camera_project", "sva_camera_inv_project", "sva_bresenham", "sva_get_camera_pairs", "sva_grid_pairs",
+    "sva_abs_diff_u8", "sva_match_literal", "sva_shift_perspective_with_disparity", "sva_improve_with_disparity",
+    "sva_disparity_to_depth", "sva_depth_from_array",
+    "sva_frame_upload", "sva_frame_set_pair_range", "sva_frame_run", "sva_frame_time", "sva_frame_kernel_times", "sva_frame_time_detailed", "sva_timer_start", "sva_timer_stop", "sva_frame_set_debug",
+    "sva_frame_download_ad", "sva_frame_download_cost", "sva_frame_download_raw_cost", "sva_frame_download_sgm",
+    "sva_frame_download_disparity", "sva_frame_ad_device_ptr", "sva_frame_mark_ad_ready",
+]
+
+_lib = None
+
+
+class SvaError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("sva error %d: %s" % (code, msg))
+        self.code = code
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError("libsva_b200.so is not built (run `python -m stereovisionarray_b200.build` or __graft_entry__.build()); "
+                              "there is no CPU fallback for the depth path")
+        L = C.CDLL(LIB_PATH)
+        L.sva_last_error.restype = C.c_char_p
+        L.sva_last_error.argtypes = [C.c_void_p]
+        L.sva_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        missing = [n for n in EXPORTS if not hasattr(L, n)]
+        if missing:
+            raise ImportError("libsva_b200.so does not export %s — rebuild it" % missing)
+        for name in EXPORTS:
+            if name != "sva_last_error":
+                getattr(L, name).restype = C.c_int
+        _lib = L
+    return _lib
+
+
+def check(ctx, rc):
+    if rc < 0:
+        msg = lib().sva_last_error(ctx).decode() if ctx else ""
+        raise SvaError(rc, msg)
+    return rc

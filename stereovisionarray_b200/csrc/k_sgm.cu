@@ -1,0 +1,394 @@
+// k_sgm.cu — K2: semi-global path aggregation; K3 (WTA + left-right check + parabolic sub-pixel) fused into the last pass.
+//
+// No counterpart in the reference: this implements the frozen spec of DESIGN.md §3.3 (Hirschmueller 2008,
+// fixed P1/P2), bit-exact against oracle/sva_oracle.c.
+//
+//   L_r(p,d) = C(p,d) + min(L_r(q,d), L_r(q,d-1)+P1, L_r(q,d+1)+P1, min_k L_r(q,k)+P2) - min_k L_r(q,k),  q = p - r
+//   S = sum_r L_r (u16; C <= 4095 and P2 <= 4095 bound L by 8190 and S over 8 paths by 65520)
+//
+// Mapping: ONE WARP PER PATH LINE per direction.  A lane owns n = 2*NR consecutive disparities packed two per register
+// (u16x2); the recurrence is DPX (VIADDMNMX.U16x2 / VIMNMX.U16x2), the d-1 / d+1 neighbours are one PRMT per register plus
+// two warp shuffles for the lane edges, and min_k is a per-lane VIMNMX tree followed by one REDUX.MIN.  Everything stays in
+// registers along the path; C is streamed with a PF-deep register prefetch ring (L1::no_allocate), S is accumulated with
+// fire-and-forget 64-bit REDs (packed u16x4 adds are carry-free by the bound above), stored plainly by the first pass and
+// only read by the last pass.  Diagonal paths use W lines of exactly H steps that wrap around the image edge and restart
+// (L = C) where the predecessor is outside the image, so every pass has uniform work per warp.
+//
+// Last pass (horizontal): S_total = S + L in registers -> packed (S<<16|d) keys -> REDUX.MIN gives the first-minimum
+// winner; S(d*-1), S(d*+1) are fetched with two shuffles for the parabola; the other view's WTA (left-right check) is a
+// systolic diagonal minimum: one key register per disparity slot shifts by one slot per step (one shuffle per step), so
+// D_o(x') = argmin_d S(y, x'+lr_gx*delta, d) falls out of the same march with no extra memory traffic.  Results of a row
+// are staged in shared memory and written coalesced by a row-end sweep that applies mask / border / cell-validity / LR.
+#include "sva_common.cuh"
+
+#define SGM_PF 8
+#define SGM_INF2 0x7FFF7FFFu
+#define SGM_WARPS 8
+#define SGM_FINAL_WARPS 4
+
+enum { SGM_MODE_STORE = 0, SGM_MODE_RED = 1, SGM_MODE_FINAL = 2 };
+
+struct SgmParams {
+    const uint16_t* C;
+    uint16_t* S;
+    int W, H, D;
+    int dx, dy;
+    uint32_t p1p1, p2p2;
+    int lanes;  // active lanes = D / (2*NR)
+    // final pass only
+    int dmin, k, gxp, gxn, gyp, gyn, lr_gx, lr_max_diff, subpixel, store_full, no_agg;
+    const uint8_t* mask;
+    uint16_t* disp;
+    float* sub;
+};
+
+template <int NR> struct Vec;
+template <> struct Vec<1> {
+    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[1]) { r[0] = ldg_stream_u32(p); }
+    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[1]) {
+        asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
+    }
+    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[1]) { *reinterpret_cast<uint32_t*>(p) = r[0]; }
+    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[1]) {
+        asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(r[0]) : "memory");
+    }
+};
+template <> struct Vec<2> {
+    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[2]) { uint2 v = ldg_stream_u64(p); r[0] = v.x; r[1] = v.y; }
+    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[2]) {
+        asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
+    }
+    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[2]) { *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]); }
+    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[2]) {
+        unsigned long long v = ((unsigned long long)r[1] << 32) | r[0];
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+    }
+};
+template <> struct Vec<4> {
+    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[4]) { uint4 v = ldg_stream_u128(p); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
+    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[4]) {
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
+    }
+    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[4]) { *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]); }
+    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[4]) {
+        unsigned long long v0 = ((unsigned long long)r[1] << 32) | r[0], v1 = ((unsigned long long)r[3] << 32) | r[2];
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v0) : "memory");
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p + 4), "l"(v1) : "memory");
+    }
+};
+
+// one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
+template <int NR>
+__device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)[NR], uint32_t& mm, uint32_t& mp2, uint32_t p1p1, uint32_t p2p2,
+                                         bool first_lane, bool last_lane) {
+    uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    if (first_lane) up = SGM_INF2;
+    if (last_lane) dn = SGM_INF2;
+    uint32_t sh[NR + 1];  // sh[j] = values at d-1 of register j; sh[j+1] = values at d+1 of register j
+    sh[0] = __byte_perm(up, L[0], 0x5432);
+#pragma unroll
+    for (int j = 1; j < NR; j++) sh[j] = __byte_perm(L[j - 1], L[j], 0x5432);
+    sh[NR] = __byte_perm(L[NR - 1], dn, 0x5432);
+    uint32_t mloc = 0xFFFFFFFFu;
+#pragma unroll
+    for (int j = 0; j < NR; j++) {
+        uint32_t t = __viaddmin_u16x2(sh[j], p1p1, L[j]);
+        t = __viaddmin_u16x2(sh[j + 1], p1p1, t);
+        t = __vminu2(t, mp2);
+        L[j] = Cc[j] + t - mm;  // both halves: t >= mm, no borrow; C + t - mm <= 8190, no carry
+        mloc = __vminu2(mloc, L[j]);
+    }
+    uint32_t m = min(mloc & 0xFFFFu, mloc >> 16);
+    m = __reduce_min_sync(0xffffffffu, m);
+    mm = m * 0x10001u;
+    mp2 = mm + p2p2;
+}
+
+struct PathPos {
+    int x, y;
+};
+
+template <int NR, int MODE>
+__global__ void __launch_bounds__(MODE == SGM_MODE_FINAL ? SGM_FINAL_WARPS * 32 : SGM_WARPS * 32)
+k_sgm_pass(SgmParams q) {
+    constexpr int NV = 2 * NR;
+    constexpr int WARPS = MODE == SGM_MODE_FINAL ? SGM_FINAL_WARPS : SGM_WARPS;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int line = blockIdx.x * WARPS + warp;
+    const int W = q.W, H = q.H, D = q.D, dx = q.dx, dy = q.dy;
+    const int nlines = dy == 0 ? H : W, len = dy == 0 ? W : H;
+    if (line >= nlines) return;
+    const bool active = lane < q.lanes;
+    const bool first_lane = lane == 0, last_lane = lane == q.lanes - 1;
+    const bool diag = dx != 0 && dy != 0;
+
+    PathPos pos, pre;  // current cell and prefetch cursor
+    if (dy == 0) { pos.y = line; pos.x = dx > 0 ? 0 : W - 1; }
+    else { pos.y = dy > 0 ? 0 : H - 1; pos.x = line; }
+    pre = pos;
+    const int lane_off = lane * NV;
+    auto cell = [&](const PathPos& p) -> long long { return ((long long)p.y * W + p.x) * D + lane_off; };
+    auto advance = [&](PathPos& p) -> bool {  // returns true when the new cell starts a fresh path (predecessor outside the image)
+        p.y += dy; p.x += dx;
+        if (dy != 0) {
+            if (p.x >= W) { p.x = 0; return true; }
+            if (p.x < 0) { p.x = W - 1; return true; }
+        }
+        return false;
+    };
+
+    uint32_t cbuf[SGM_PF][NR], sbuf[MODE == SGM_MODE_FINAL ? SGM_PF : 1][NR];
+#pragma unroll
+    for (int u = 0; u < SGM_PF; u++) {
+#pragma unroll
+        for (int j = 0; j < NR; j++) { cbuf[u][j] = SGM_INF2; if (MODE == SGM_MODE_FINAL) sbuf[u][j] = 0; }
+        if (u < len) {
+            if (active) {
+                Vec<NR>::load(q.C + cell(pre), cbuf[u]);
+                if (MODE == SGM_MODE_FINAL && !q.no_agg) Vec<NR>::load_rw(q.S + cell(pre), sbuf[u]);
+            }
+            advance(pre);
+        }
+    }
+
+    uint32_t L[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) L[j] = 0;
+    uint32_t mm = 0, mp2 = q.p2p2;
+    bool restart = true;
+
+    // ---- final-pass state ----
+    extern __shared__ unsigned char smem_raw[];
+    uint16_t* pend_d = nullptr; float* pend_sub = nullptr; uint16_t* other_row = nullptr;
+    uint32_t acc[NV];
+    const int tdir = q.lr_gx * dx;  // +1: LR entries travel towards larger d; -1: towards smaller d
+    if (MODE == SGM_MODE_FINAL) {
+        unsigned char* base = smem_raw + (size_t)warp * (8 * (size_t)W);
+        pend_sub = reinterpret_cast<float*>(base);
+        pend_d = reinterpret_cast<uint16_t*>(base + 4 * (size_t)W);
+        other_row = reinterpret_cast<uint16_t*>(base + 6 * (size_t)W);
+        for (int x = lane; x < W; x += 32) other_row[x] = 0xFFFFu;
+#pragma unroll
+        for (int i = 0; i < NV; i++) acc[i] = 0xFFFFFFFFu;
+        __syncwarp();
+    }
+
+    for (int s0 = 0; s0 < len; s0 += SGM_PF) {
+#pragma unroll
+        for (int u = 0; u < SGM_PF; u++) {
+            const int s = s0 + u;
+            if (s >= len) break;
+            uint32_t Cc[NR], Sp[NR];
+#pragma unroll
+            for (int j = 0; j < NR; j++) { Cc[j] = cbuf[u][j]; if (MODE == SGM_MODE_FINAL) Sp[j] = sbuf[u][j]; }
+            if (s + SGM_PF < len) {
+                if (active) {
+                    Vec<NR>::load(q.C + cell(pre), cbuf[u]);
+                    if (MODE == SGM_MODE_FINAL && !q.no_agg) Vec<NR>::load_rw(q.S + cell(pre), sbuf[u]);
+                }
+                advance(pre);
+            }
+            if (restart || (MODE == SGM_MODE_FINAL && q.no_agg)) {
+#pragma unroll
+                for (int j = 0; j < NR; j++) L[j] = 0;
+                mm = 0; mp2 = q.p2p2;
+            }
+            sgm_step<NR>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+
+            if (MODE == SGM_MODE_STORE) {
+                if (active) Vec<NR>::store(q.S + cell(pos), L);
+            } else if (MODE == SGM_MODE_RED) {
+                if (active) Vec<NR>::red(q.S + cell(pos), L);
+            } else {
+                // ---- fused K3 ----
+                uint32_t St[NR];
+#pragma unroll
+                for (int j = 0; j < NR; j++) St[j] = q.no_agg ? L[j] : Sp[j] + L[j];
+                if (q.store_full && active) Vec<NR>::store(q.S + cell(pos), St);
+                uint32_t key[NV];
+                uint32_t kbest = 0xFFFFFFFFu;
+#pragma unroll
+                for (int j = 0; j < NR; j++) {
+                    key[2 * j] = active ? ((St[j] << 16) | (uint32_t)(lane_off + 2 * j)) : 0xFFFFFFFFu;
+                    key[2 * j + 1] = active ? ((St[j] & 0xFFFF0000u) | (uint32_t)(lane_off + 2 * j + 1)) : 0xFFFFFFFFu;
+                    kbest = min(kbest, min(key[2 * j], key[2 * j + 1]));
+                }
+                kbest = __reduce_min_sync(0xffffffffu, kbest);
+                const int dstar = (int)(kbest & 0xFFFFu);
+                float fsub = (float)dstar;
+                if (q.subpixel && dstar > 0 && dstar < D - 1) {  // warp-uniform
+                    const int dl = dstar - 1, dr = dstar + 1;
+                    uint32_t vl = St[0], vr = St[0];
+#pragma unroll
+                    for (int j = 1; j < NR; j++) {
+                        if (((dl >> 1) % NR) == j) vl = St[j];
+                        if (((dr >> 1) % NR) == j) vr = St[j];
+                    }
+                    vl = __shfl_sync(0xffffffffu, vl, dl / NV);
+                    vr = __shfl_sync(0xffffffffu, vr, dr / NV);
+                    const int sl = (dl & 1) ? (int)(vl >> 16) : (int)(vl & 0xFFFFu);
+                    const int sr = (dr & 1) ? (int)(vr >> 16) : (int)(vr & 0xFFFFu);
+                    const int s0v = (int)(kbest >> 16);
+                    const int den = sl - 2 * s0v + sr;
+                    if (den > 0) fsub = (float)dstar + (float)(sl - sr) / (float)(2 * den);
+                }
+                if (lane == 0) { pend_d[pos.x] = (uint16_t)dstar; pend_sub[pos.x] = fsub; }
+                if (q.lr_gx != 0) {
+                    if (tdir > 0) {
+                        uint32_t carry = __shfl_up_sync(0xffffffffu, acc[NV - 1], 1);
+                        if (first_lane) carry = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = NV - 1; i > 0; i--) acc[i] = acc[i - 1];
+                        acc[0] = carry;
+                    } else {
+                        uint32_t carry = __shfl_down_sync(0xffffffffu, acc[0], 1);
+                        if (last_lane) carry = 0xFFFFFFFFu;
+#pragma unroll
+                        for (int i = 0; i < NV - 1; i++) acc[i] = acc[i + 1];
+                        acc[NV - 1] = carry;
+                    }
+#pragma unroll
+                    for (int i = 0; i < NV; i++) acc[i] = min(acc[i], key[i]);
+                    // the entry leaving the volume this step is complete
+                    if (tdir > 0 && last_lane) {
+                        int xo = pos.x - q.lr_gx * (q.dmin + D - 1);
+                        if (xo >= 0 && xo < W) other_row[xo] = (uint16_t)(acc[NV - 1] & 0xFFFFu);
+                    }
+                    if (tdir < 0 && first_lane) {
+                        int xo = pos.x - q.lr_gx * q.dmin;
+                        if (xo >= 0 && xo < W) other_row[xo] = (uint16_t)(acc[0] & 0xFFFFu);
+                    }
+                }
+            }
+            if (s + 1 < len) restart = advance(pos);
+        }
+    }
+
+    if (MODE == SGM_MODE_FINAL) {
+        // flush the LR entries still inside the volume at the end of the row (they have seen every in-image contribution)
+        if (q.lr_gx != 0 && active) {
+#pragma unroll
+            for (int i = 0; i < NV; i++) {
+                int xo = pos.x - q.lr_gx * (q.dmin + lane_off + i);
+                if (xo >= 0 && xo < W && acc[i] != 0xFFFFFFFFu) other_row[xo] = (uint16_t)(acc[i] & 0xFFFFu);
+            }
+        }
+        __syncwarp();
+        const int y = pos.y, k = q.k;
+        int limy = 0x7FFFFFFF;
+        bool row_in = y >= k && y < H - k;
+        if (q.gyp > 0) limy = min(limy, (y - k) / q.gyp);
+        if (q.gyn > 0) limy = min(limy, (H - k - y) / q.gyn);
+        for (int x = lane; x < W; x += 32) {
+            const int d = pend_d[x];
+            const int delta = q.dmin + d;
+            bool ok = row_in && x >= k && x < W - k;
+            if (ok && q.mask) ok = q.mask[(size_t)y * W + x] != 0;
+            if (ok) {
+                int lim = limy;
+                if (q.gxp > 0) lim = min(lim, (x - k) / q.gxp);
+                if (q.gxn > 0) lim = min(lim, (W - k - x) / q.gxn);
+                ok = delta <= lim;
+            }
+            if (ok && q.lr_gx != 0) {
+                int xo = x - q.lr_gx * delta;
+                if (xo < 0 || xo >= W) ok = false;
+                else {
+                    int od = other_row[xo];
+                    ok = od != 0xFFFF && abs(d - od) <= q.lr_max_diff;
+                }
+            }
+            q.disp[(size_t)y * W + x] = ok ? (uint16_t)delta : (uint16_t)SVA_DISP_INVALID;
+            if (q.sub) q.sub[(size_t)y * W + x] = ok ? (float)q.dmin + pend_sub[x] : SVA_SUBPIX_INVALID;
+        }
+    }
+}
+
+template <int NR>
+static int launch_pass(sva_ctx* ctx, const SgmParams& q, int mode) {
+    const int nlines = q.dy == 0 ? q.H : q.W;
+    if (mode == SGM_MODE_FINAL) {
+        size_t smem = (size_t)SGM_FINAL_WARPS * 8 * q.W;
+        if (smem > 200 * 1024) return ctx->fail(SVA_ERR_BAD_ARG, "image too wide for the fused final pass (W > 6400)");
+        SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchScope ls(ctx, "k_sgm_final");
+        k_sgm_pass<NR, SGM_MODE_FINAL><<<div_up(nlines, SGM_FINAL_WARPS), SGM_FINAL_WARPS * 32, smem, ctx->stream>>>(q);
+    } else if (mode == SGM_MODE_STORE) {
+        LaunchScope ls(ctx, q.dy == 0 ? "k_sgm_store_h" : (q.dx == 0 ? "k_sgm_store_v" : "k_sgm_store_d"));
+        k_sgm_pass<NR, SGM_MODE_STORE><<<div_up(nlines, SGM_WARPS), SGM_WARPS * 32, 0, ctx->stream>>>(q);
+    } else {
+        LaunchScope ls(ctx, q.dy == 0 ? "k_sgm_red_h" : (q.dx == 0 ? "k_sgm_red_v" : "k_sgm_red_d"));
+        k_sgm_pass<NR, SGM_MODE_RED><<<div_up(nlines, SGM_WARPS), SGM_WARPS * 32, 0, ctx->stream>>>(q);
+    }
+    SVA_CUDA_OK(ctx, cudaGetLastError());
+    return SVA_OK;
+}
+
+static int launch_pass_nr(sva_ctx* ctx, const SgmParams& q, int nr, int mode) {
+    switch (nr) {
+        case 1: return launch_pass<1>(ctx, q, mode);
+        case 2: return launch_pass<2>(ctx, q, mode);
+        default: return launch_pass<4>(ctx, q, mode);
+    }
+}
+
+// smallest n in {2,4,8} disparities per lane with D % n == 0 and D / n <= 32
+int sva_sgm_regs_per_lane(int D) {
+    for (int n = 2; n <= 8; n *= 2)
+        if (D % n == 0 && D / n <= 32) return n / 2;
+    return 0;
+}
+
+// Pass order (oracle direction indices in ORC_DIRS order: 0 v+, 1 v-, 2 h+, 3 h-, 4..7 diagonals):
+//   8 paths: 0 (store), 1, 4, 5, 6, 7, 2 (RED), 3 (final)     4 paths: 0 (store), 1, 2 (RED), 3 (final)
+static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+
+int sva_run_sgm(sva_ctx* ctx) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp;
+    const int nr = sva_sgm_regs_per_lane(D);
+    if (nr == 0) return ctx->fail(SVA_ERR_BAD_ARG, "num_disp must be a multiple of 2 with D/8 <= 32 (8..256)");
+    size_t cells = (size_t)W * H * D;
+    SVA_TRY(ctx->reserve(ctx->S, cells * sizeof(uint16_t) + 64));
+    SVA_TRY(ctx->reserve(ctx->disp, (size_t)W * H * sizeof(uint16_t)));
+    SVA_TRY(ctx->reserve(ctx->subpix, (size_t)W * H * sizeof(float)));
+    SgmParams q{};
+    q.C = ctx->C.as<uint16_t>(); q.S = ctx->S.as<uint16_t>(); q.W = W; q.H = H; q.D = D;
+    q.p1p1 = (uint32_t)p.p1 * 0x10001u; q.p2p2 = (uint32_t)p.p2 * 0x10001u;
+    q.lanes = D / (2 * nr);
+    q.dmin = p.min_disp; q.k = p.win_half; q.lr_gx = p.lr_gx; q.lr_max_diff = p.lr_max_diff; q.subpixel = p.subpixel;
+    q.store_full = ctx->debug_store_full_s ? 1 : 0;
+    q.mask = ctx->has_mask ? ctx->mask.as<uint8_t>() : nullptr;
+    q.disp = ctx->disp.as<uint16_t>(); q.sub = ctx->subpix.as<float>();
+    for (int i = 0; i < p.n_pairs; i++) {
+        int gx = p.pair_gx[i], gy = p.pair_gy[i];
+        if (gx > 0) q.gxp = gx > q.gxp ? gx : q.gxp;
+        if (gx < 0) q.gxn = -gx > q.gxn ? -gx : q.gxn;
+        if (gy > 0) q.gyp = gy > q.gyp ? gy : q.gyp;
+        if (gy < 0) q.gyn = -gy > q.gyn ? -gy : q.gyn;
+    }
+    if (ctx->sgm_dir_mask_override) {  // test hook: accumulate exactly these directions, no final pass
+        bool first = true;
+        for (int i = 0; i < 8; i++) {
+            if (!(ctx->sgm_dir_mask_override & (1u << i))) continue;
+            q.dx = DIRS[i][0]; q.dy = DIRS[i][1];
+            SVA_TRY(launch_pass_nr(ctx, q, nr, first ? SGM_MODE_STORE : SGM_MODE_RED));
+            first = false;
+        }
+        ctx->have_sgm = true;
+        return SVA_OK;
+    }
+    static const int order8[8] = {0, 1, 4, 5, 6, 7, 2, 3}, order4[4] = {0, 1, 2, 3};
+    const int n = p.n_paths;
+    const int* order = n == 8 ? order8 : order4;
+    for (int i = 0; i + 1 < n; i++) {
+        q.dx = DIRS[order[i]][0]; q.dy = DIRS[order[i]][1];
+        SVA_TRY(launch_pass_nr(ctx, q, nr, i == 0 ? SGM_MODE_STORE : SGM_MODE_RED));
+    }
+    q.dx = -1; q.dy = 0;
+    q.no_agg = n == 0 ? 1 : 0;
+    SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_FINAL));
+    ctx->have_sgm = true; ctx->have_disp = true;
+    return SVA_OK;
+}

@@ -1,0 +1,241 @@
+// sva_api.cu — extern "C" entry points of the volume-mode pipeline (staged / device-resident and host-buffer forms).
+#include <cstring>
+
+#include "sva_common.cuh"
+
+int sva_build_line_images(sva_ctx* ctx);
+int sva_run_ad(sva_ctx* ctx);
+int sva_run_box(sva_ctx* ctx, bool raw);
+int sva_run_sgm(sva_ctx* ctx);
+int sva_sgm_regs_per_lane(int D);
+
+static int check_params(sva_ctx* c, const sva_params* p) {
+    if (!p) return c->fail(SVA_ERR_BAD_ARG, "null params");
+    if (p->width < 8 || p->height < 8) return c->fail(SVA_ERR_BAD_ARG, "image smaller than 8x8");
+    if (p->num_disp < 8 || p->num_disp > 256 || p->num_disp % 8) return c->fail(SVA_ERR_BAD_ARG, "num_disp must be a multiple of 8 in 8..256");
+    if (p->min_disp < 0 || p->min_disp > 4096) return c->fail(SVA_ERR_BAD_ARG, "min_disp must be in 0..4096");
+    if (p->win_half < 1 || p->win_half > 56) return c->fail(SVA_ERR_BAD_ARG, "win_half must be in 1..56");
+    if (p->n_pairs < 1 || p->n_pairs > SVA_MAX_PAIRS) return c->fail(SVA_ERR_BAD_ARG, "n_pairs must be in 1..32");
+    if (p->cost_cap < 1 || p->cost_cap > SVA_COST_CAP_MAX || p->cost_shift < 0 || p->cost_shift > 31) return c->fail(SVA_ERR_BAD_ARG, "bad cost_cap / cost_shift");
+    if (p->p1 < 0 || p->p2 < p->p1 || p->p2 > 4095) return c->fail(SVA_ERR_BAD_ARG, "need 0 <= p1 <= p2 <= 4095");
+    if (p->n_paths != 0 && p->n_paths != 4 && p->n_paths != 8) return c->fail(SVA_ERR_BAD_ARG, "n_paths must be 0, 4 or 8");
+    if (p->lr_gx < -1 || p->lr_gx > 1) return c->fail(SVA_ERR_BAD_ARG, "lr_gx must be -1, 0 or +1");
+    if (sva_sgm_regs_per_lane(p->num_disp) == 0) return c->fail(SVA_ERR_BAD_ARG, "unsupported num_disp");
+    // exact u32 box sums: 4k^2 * 255 * n_pairs must fit
+    if (4.0 * p->win_half * p->win_half * 255.0 * p->n_pairs > 4.0e9) return c->fail(SVA_ERR_BAD_ARG, "window sum overflows u32");
+    return SVA_OK;
+}
+
+static int check_image(sva_ctx* c, const sva_image_u8* im, int W, int H, const char* what) {
+    if (!im || !im->data) return c->fail(SVA_ERR_BAD_ARG, std::string("null image: ") + what);
+    if (im->cols != W || im->rows != H || im->step < (size_t)W) return c->fail(SVA_ERR_BAD_ARG, std::string("image size / step mismatch: ") + what);
+    return SVA_OK;
+}
+
+extern "C" {
+
+int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(check_params(c, p));
+    const int W = p->width, H = p->height;
+    SVA_TRY(check_image(c, ref, W, H, "ref"));
+    if (!others) return c->fail(SVA_ERR_BAD_ARG, "null others");
+    for (int i = 0; i < p->n_pairs; i++) SVA_TRY(check_image(c, &others[i], W, H, "other view"));
+    if (mask) SVA_TRY(check_image(c, mask, W, H, "mask"));
+    c->prm = *p;
+    c->pair_begin = 0; c->pair_end = p->n_pairs;
+    c->have_frame = c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;
+    const size_t img = (size_t)W * H;
+    SVA_TRY(c->reserve(c->ref_img, img));
+    SVA_TRY(c->reserve(c->other_imgs, img * p->n_pairs));
+    SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->ref_img.p, W, ref->data, ref->step, W, H, cudaMemcpyHostToDevice, c->stream));
+    for (int i = 0; i < p->n_pairs; i++)
+        SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->other_imgs.as<uint8_t>() + img * i, W, others[i].data, others[i].step, W, H, cudaMemcpyHostToDevice, c->stream));
+    c->has_mask = mask != nullptr;
+    if (mask) {
+        SVA_TRY(c->reserve(c->mask, img));
+        SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->mask.p, W, mask->data, mask->step, W, H, cudaMemcpyHostToDevice, c->stream));
+    }
+    SVA_TRY(sva_build_line_images(c));
+    c->have_frame = true;
+    return SVA_OK;
+}
+
+int sva_frame_set_pair_range(sva_ctx* c, int32_t b, int32_t e) {
+    if (!c || !c->have_frame) return c ? c->fail(SVA_ERR_STATE, "no frame uploaded") : SVA_ERR_BAD_ARG;
+    if (b < 0 || e > c->prm.n_pairs || b > e) return c->fail(SVA_ERR_BAD_ARG, "bad pair range");
+    c->pair_begin = b; c->pair_end = e;
+    return SVA_OK;
+}
+
+int sva_frame_set_debug(sva_ctx* c, int32_t store_full_s, uint32_t sgm_dir_mask) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    c->debug_store_full_s = store_full_s != 0;
+    c->sgm_dir_mask_override = sgm_dir_mask;
+    return SVA_OK;
+}
+
+static int run_stage(sva_ctx* c, int stage) {
+    switch (stage) {
+        case SVA_STAGE_AD:
+            if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+            return sva_run_ad(c);
+        case SVA_STAGE_BOX:
+            if (!c->have_ad) return c->fail(SVA_ERR_STATE, "AD volume not computed");
+            return sva_run_box(c, false);
+        case SVA_STAGE_SGM:
+            if (!c->have_cost) return c->fail(SVA_ERR_STATE, "cost volume not computed");
+            return sva_run_sgm(c);
+        case SVA_STAGE_ALL:
+            SVA_TRY(run_stage(c, SVA_STAGE_AD));
+            SVA_TRY(run_stage(c, SVA_STAGE_BOX));
+            return run_stage(c, SVA_STAGE_SGM);
+        default: return c->fail(SVA_ERR_BAD_ARG, "unknown stage");
+    }
+}
+
+int sva_frame_run(sva_ctx* c, int32_t stage) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    return run_stage(c, stage);
+}
+
+int sva_frame_time(sva_ctx* c, int32_t stage, int32_t iters, float* out_ms) {
+    if (!c || !out_ms || iters < 1) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    cudaEvent_t e0, e1;
+    SVA_CUDA_OK(c, cudaEventCreate(&e0));
+    SVA_CUDA_OK(c, cudaEventCreate(&e1));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    SVA_CUDA_OK(c, cudaEventRecord(e0, c->stream));
+    int rc = SVA_OK;
+    for (int i = 0; i < iters && rc == SVA_OK; i++) rc = run_stage(c, stage);
+    SVA_CUDA_OK(c, cudaEventRecord(e1, c->stream));
+    SVA_CUDA_OK(c, cudaEventSynchronize(e1));
+    SVA_CUDA_OK(c, cudaEventElapsedTime(out_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    return rc;
+}
+
+/* like sva_frame_time, with a CUDA-event pair around every kernel: per distinct kernel name the summed time and launch count */
+int sva_frame_time_detailed(sva_ctx* c, int32_t stage, int32_t iters, float* out_total_ms, const char** names, float* sum_ms, int32_t* counts, int32_t cap) {
+    if (!c || !out_total_ms || iters < 1) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    c->ktimes.clear(); c->events_used = 0;
+    cudaEvent_t e0, e1;
+    SVA_CUDA_OK(c, cudaEventCreate(&e0));
+    SVA_CUDA_OK(c, cudaEventCreate(&e1));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    c->timing = true;
+    SVA_CUDA_OK(c, cudaEventRecord(e0, c->stream));
+    int rc = SVA_OK;
+    for (int i = 0; i < iters && rc == SVA_OK; i++) rc = run_stage(c, stage);
+    SVA_CUDA_OK(c, cudaEventRecord(e1, c->stream));
+    c->timing = false;
+    SVA_CUDA_OK(c, cudaEventSynchronize(e1));
+    SVA_CUDA_OK(c, cudaEventElapsedTime(out_total_ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    if (rc != SVA_OK) return rc;
+    int n = 0;
+    for (const KernelTime& kt : c->ktimes) {
+        float ms = 0;
+        SVA_CUDA_OK(c, cudaEventElapsedTime(&ms, kt.beg, kt.end));
+        int j = 0;
+        for (; j < n; j++) if (names[j] == kt.name) break;
+        if (j == n) { if (n >= cap) continue; names[n] = kt.name; sum_ms[n] = 0; counts[n] = 0; n++; }
+        sum_ms[j] += ms; counts[j]++;
+    }
+    return n;
+}
+
+/* CUDA-event stopwatch on the ctx stream, for timing a sequence of host-buffer calls (the e2e path) on the device clock */
+int sva_timer_start(sva_ctx* c) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    while (c->event_pool.size() < 2) { cudaEvent_t e; SVA_CUDA_OK(c, cudaEventCreate(&e)); c->event_pool.push_back(e); }
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    SVA_CUDA_OK(c, cudaEventRecord(c->event_pool[0], c->stream));
+    return SVA_OK;
+}
+int sva_timer_stop(sva_ctx* c, float* out_ms) {
+    if (!c || !out_ms || c->event_pool.size() < 2) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaEventRecord(c->event_pool[1], c->stream));
+    SVA_CUDA_OK(c, cudaEventSynchronize(c->event_pool[1]));
+    SVA_CUDA_OK(c, cudaEventElapsedTime(out_ms, c->event_pool[0], c->event_pool[1]));
+    return SVA_OK;
+}
+
+int sva_frame_kernel_times(sva_ctx* c, int32_t stage, const char** names, float* ms, int32_t cap) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    c->ktimes.clear(); c->events_used = 0;
+    c->timing = true;
+    int rc = run_stage(c, stage);
+    c->timing = false;
+    if (rc != SVA_OK) return rc;
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    int n = (int)c->ktimes.size();
+    for (int i = 0; i < n && i < cap; i++) {
+        if (names) names[i] = c->ktimes[i].name;
+        if (ms) SVA_CUDA_OK(c, cudaEventElapsedTime(&ms[i], c->ktimes[i].beg, c->ktimes[i].end));
+    }
+    return n;
+}
+
+static int download(sva_ctx* c, bool have, const DevBuf& b, void* out, size_t bytes, const char* what) {
+    if (!c || !out) return SVA_ERR_BAD_ARG;
+    if (!have) return c->fail(SVA_ERR_STATE, std::string("not computed yet: ") + what);
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_CUDA_OK(c, cudaMemcpyAsync(out, b.p, bytes, cudaMemcpyDeviceToHost, c->stream));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SVA_OK;
+}
+
+static size_t cells(const sva_ctx* c) { return (size_t)c->prm.width * c->prm.height * c->prm.num_disp; }
+
+int sva_frame_download_ad(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_ad, c->A, out, cells(c) * 2, "AD volume"); }
+int sva_frame_download_cost(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_cost, c->C, out, cells(c) * 2, "cost volume"); }
+int sva_frame_download_sgm(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_sgm, c->S, out, cells(c) * 2, "aggregated volume"); }
+int sva_frame_download_raw_cost(sva_ctx* c, uint32_t* out) {
+    if (!c || !out) return SVA_ERR_BAD_ARG;
+    if (!c->have_ad) return c->fail(SVA_ERR_STATE, "AD volume not computed");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(sva_run_box(c, true));
+    return download(c, true, c->Craw, out, cells(c) * 4, "raw cost");
+}
+int sva_frame_download_disparity(sva_ctx* c, uint16_t* out_disp, float* out_sub) {
+    if (!c || !out_disp) return SVA_ERR_BAD_ARG;
+    if (!c->have_disp) return c->fail(SVA_ERR_STATE, "disparity not computed");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    size_t px = (size_t)c->prm.width * c->prm.height;
+    SVA_CUDA_OK(c, cudaMemcpyAsync(out_disp, c->disp.p, px * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (out_sub) SVA_CUDA_OK(c, cudaMemcpyAsync(out_sub, c->subpix.p, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SVA_OK;
+}
+
+int sva_frame_ad_device_ptr(sva_ctx* c, void** out_ptr, size_t* out_bytes) {
+    if (!c || !out_ptr || !out_bytes) return SVA_ERR_BAD_ARG;
+    if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(c->reserve(c->A, cells(c) * 2));
+    *out_ptr = c->A.p; *out_bytes = cells(c) * 2;
+    return SVA_OK;
+}
+/* after an external (cross-GPU) reduction wrote the full A volume into the buffer above */
+int sva_frame_mark_ad_ready(sva_ctx* c) {
+    if (!c || !c->have_frame) return SVA_ERR_BAD_ARG;
+    c->have_ad = true;
+    return SVA_OK;
+}
+
+int sva_depth_from_array(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask,
+                         uint16_t* out_disp, float* out_subpix) {
+    if (!c || !out_disp) return SVA_ERR_BAD_ARG;
+    SVA_TRY(sva_frame_upload(c, p, ref, others, mask));
+    SVA_TRY(run_stage(c, SVA_STAGE_ALL));
+    return sva_frame_download_disparity(c, out_disp, out_subpix);
+}
+
+}  // extern "C"

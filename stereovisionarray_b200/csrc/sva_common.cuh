@@ -1,0 +1,110 @@
+// sva_common.cuh — context, error handling and small device helpers shared by the sm_100a kernels.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/sva_c_api.h"
+
+#define SVA_CUDA_OK(ctx, expr)                                                                         \
+    do {                                                                                               \
+        cudaError_t e__ = (expr);                                                                      \
+        if (e__ != cudaSuccess) return (ctx)->fail(SVA_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(e__)); \
+    } while (0)
+
+#define SVA_TRY(expr)            \
+    do {                         \
+        int rc__ = (expr);       \
+        if (rc__ != SVA_OK) return rc__; \
+    } while (0)
+
+// One growable device buffer.
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    template <typename T> T* as() const { return (T*)p; }
+};
+
+// Per-pair "line image": the other view re-laid out so that walking the disparity walks +g bytes along a row (k_ad.cu).
+struct PairGeom {
+    int32_t alpha, beta, base;  // byte offset of ref pixel (x,y) at delta=0:  base + x*alpha + y*beta
+    int32_t g;                  // bytes per unit disparity (gcd(|gx|,|gy|))
+    int32_t rows, pitch;        // line-image size
+    int32_t a, b, u, v, cmin, tmin, pad;
+    size_t offset;              // byte offset of this pair's line image inside ctx->lines
+};
+
+struct KernelTime {
+    const char* name;
+    cudaEvent_t beg, end;
+};
+
+struct sva_ctx {
+    int device = 0;
+    int sm_count = 148;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    std::string err;
+    uint64_t launches = 0;
+
+    // ---- resident frame state (volume mode) ----
+    bool have_frame = false, have_ad = false, have_cost = false, have_sgm = false, have_disp = false;
+    sva_params prm{};
+    int pair_begin = 0, pair_end = 0;
+    bool has_mask = false;
+    bool debug_store_full_s = false;
+    uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
+    PairGeom geom[SVA_MAX_PAIRS];
+    DevBuf ref_img, other_imgs, lines, mask, A, C, Craw, S, disp, subpix, other_d, scratch, scratch2;
+    DevBuf staging_host;  // pinned host staging for image uploads / result downloads
+
+    // ---- per-kernel timing of the last run ----
+    bool timing = false;
+    std::vector<KernelTime> ktimes;
+    std::vector<cudaEvent_t> event_pool;
+    size_t events_used = 0;
+
+    int fail(int code, const std::string& msg) {
+        err = msg;
+        return code;
+    }
+    int reserve(DevBuf& b, size_t bytes);
+    int reserve_pinned(DevBuf& b, size_t bytes);
+    void time_begin(const char* name);
+    void time_end();
+};
+
+// RAII-ish helper: records an event pair around a kernel when ctx->timing is on, and counts the launch.
+struct LaunchScope {
+    sva_ctx* c;
+    LaunchScope(sva_ctx* ctx, const char* name) : c(ctx) {
+        c->launches++;
+        if (c->timing) c->time_begin(name);
+    }
+    ~LaunchScope() {
+        if (c->timing) c->time_end();
+    }
+};
+
+static inline int div_up(int a, int b) { return (a + b - 1) / b; }
+
+#ifdef __CUDACC__
+// streaming (read-once) global loads: bypass L1 allocation
+__device__ __forceinline__ uint32_t ldg_stream_u32(const void* p) {
+    uint32_t v;
+    asm volatile("ld.global.nc.L1::no_allocate.u32 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint2 ldg_stream_u64(const void* p) {
+    uint2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ uint4 ldg_stream_u128(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+#endif

@@ -1,0 +1,102 @@
+// sva_ctx.cu — context lifetime, HBM workspaces, event-based kernel timing.
+#include <cstdio>
+
+#include "sva_common.cuh"
+
+int sva_ctx::reserve(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return SVA_OK;
+    if (b.p) {
+        cudaStreamSynchronize(stream);
+        cudaFree(b.p);
+        b.p = nullptr; b.bytes = 0;
+    }
+    size_t want = (bytes + 255) & ~(size_t)255;
+    cudaError_t e = cudaMalloc(&b.p, want);
+    if (e != cudaSuccess) {
+        b.p = nullptr;
+        return fail(e == cudaErrorMemoryAllocation ? SVA_ERR_NOMEM : SVA_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    }
+    b.bytes = want;
+    return SVA_OK;
+}
+
+int sva_ctx::reserve_pinned(DevBuf& b, size_t bytes) {
+    if (b.bytes >= bytes && b.p) return SVA_OK;
+    if (b.p) { cudaStreamSynchronize(stream); cudaFreeHost(b.p); b.p = nullptr; b.bytes = 0; }
+    cudaError_t e = cudaMallocHost(&b.p, bytes);
+    if (e != cudaSuccess) { b.p = nullptr; return fail(SVA_ERR_NOMEM, std::string("cudaMallocHost: ") + cudaGetErrorString(e)); }
+    b.bytes = bytes;
+    return SVA_OK;
+}
+
+void sva_ctx::time_begin(const char* name) {
+    while (event_pool.size() < events_used + 2) {
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        event_pool.push_back(e);
+    }
+    KernelTime kt{name, event_pool[events_used], event_pool[events_used + 1]};
+    events_used += 2;
+    cudaEventRecord(kt.beg, stream);
+    ktimes.push_back(kt);
+}
+
+void sva_ctx::time_end() { cudaEventRecord(ktimes.back().end, stream); }
+
+extern "C" {
+
+int sva_api_version(void) { return SVA_API_VERSION; }
+
+int sva_create(int device, sva_ctx** out) {
+    if (!out) return SVA_ERR_BAD_ARG;
+    *out = nullptr;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return SVA_ERR_NO_DEVICE;
+    cudaDeviceProp prop;
+    if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return SVA_ERR_CUDA;
+    if (prop.major != 10) return SVA_ERR_NO_DEVICE;  // built for sm_100a only; there is no fallback path
+    if (cudaSetDevice(device) != cudaSuccess) return SVA_ERR_CUDA;
+    sva_ctx* c = new sva_ctx();
+    c->device = device;
+    c->sm_count = prop.multiProcessorCount;
+    if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SVA_ERR_CUDA; }
+    c->stream = c->own_stream;
+    *out = c;
+    return SVA_OK;
+}
+
+int sva_destroy(sva_ctx* c) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    cudaSetDevice(c->device);
+    cudaStreamSynchronize(c->stream);
+    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2};
+    for (DevBuf* b : bufs)
+        if (b->p) cudaFree(b->p);
+    if (c->staging_host.p) cudaFreeHost(c->staging_host.p);
+    for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
+    cudaStreamDestroy(c->own_stream);
+    delete c;
+    return SVA_OK;
+}
+
+const char* sva_last_error(const sva_ctx* c) { return c ? c->err.c_str() : "null context"; }
+
+int sva_set_stream(sva_ctx* c, void* s) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    return SVA_OK;
+}
+
+int sva_synchronize(sva_ctx* c) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SVA_OK;
+}
+
+int sva_kernel_launches(const sva_ctx* c, uint64_t* out) {
+    if (!c || !out) return SVA_ERR_BAD_ARG;
+    *out = c->launches;
+    return SVA_OK;
+}
+
+}  // extern "C"

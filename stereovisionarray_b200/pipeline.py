@@ -1,0 +1,147 @@
+"""Host-side driver of the volume-mode depth pipeline over the C ABI (one DepthContext per GPU).
+
+Stages: K1a AD volume -> K1b box/pack -> K2 SGM passes with K3 (WTA / LR / sub-pixel) fused in the last one.
+All compute happens in libsva_b200.so on the GPU; this module only marshals numpy buffers."""
+import ctypes as C
+
+import numpy as np
+
+from . import abi
+from ._lib import check, lib
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class DepthContext:
+    def __init__(self, device=0):
+        self._L = lib()
+        h = C.c_void_p()
+        rc = self._L.sva_create(device, C.byref(h))
+        if rc != 0:
+            raise RuntimeError("sva_create(device=%d) failed with %d — a B200 (sm_100) GPU is required; there is no CPU fallback" % (device, rc))
+        self._h = h
+        self.params = None
+
+    def close(self):
+        if self._h:
+            self._L.sva_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- staged / resident ----
+    def upload(self, p, ref, others, mask=None):
+        r, rk = abi.image_u8(np.ascontiguousarray(ref, dtype=np.uint8) if not isinstance(ref, np.ndarray) or ref.dtype != np.uint8 else ref)
+        o, ok = abi.image_array(others) if not isinstance(others, tuple) else others
+        m = None
+        if mask is not None:
+            m, mk = abi.image_u8(mask)
+        check(self._h, self._L.sva_frame_upload(self._h, C.byref(p), C.byref(r), o, C.byref(m) if m is not None else None))
+        self.params = p
+
+    def set_pair_range(self, b, e):
+        check(self._h, self._L.sva_frame_set_pair_range(self._h, b, e))
+
+    def set_debug(self, store_full_s=0, sgm_dir_mask=0):
+        check(self._h, self._L.sva_frame_set_debug(self._h, int(store_full_s), C.c_uint32(sgm_dir_mask)))
+
+    def run(self, stage=abi.STAGE_ALL):
+        check(self._h, self._L.sva_frame_run(self._h, stage))
+
+    def time(self, stage, iters):
+        ms = C.c_float()
+        check(self._h, self._L.sva_frame_time(self._h, stage, iters, C.byref(ms)))
+        return ms.value
+
+    def kernel_times(self, stage=abi.STAGE_ALL):
+        names = (C.c_char_p * 64)()
+        ms = (C.c_float * 64)()
+        n = check(self._h, self._L.sva_frame_kernel_times(self._h, stage, names, ms, 64))
+        return [(names[i].decode(), ms[i]) for i in range(min(n, 64))]
+
+    def time_detailed(self, stage, iters):
+        """-> (total_ms, {kernel name: (sum_ms, launches)}) with CUDA events on the ctx stream"""
+        names = (C.c_char_p * 64)()
+        sums = (C.c_float * 64)()
+        cnts = (C.c_int32 * 64)()
+        tot = C.c_float()
+        n = check(self._h, self._L.sva_frame_time_detailed(self._h, stage, iters, C.byref(tot), names, sums, cnts, 64))
+        return tot.value, {names[i].decode(): (sums[i], cnts[i]) for i in range(n)}
+
+    def timer_start(self):
+        check(self._h, self._L.sva_timer_start(self._h))
+
+    def timer_stop(self):
+        ms = C.c_float()
+        check(self._h, self._L.sva_timer_stop(self._h, C.byref(ms)))
+        return ms.value
+
+    def synchronize(self):
+        check(self._h, self._L.sva_synchronize(self._h))
+
+    def set_stream(self, stream_ptr):
+        check(self._h, self._L.sva_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def launches(self):
+        n = C.c_uint64()
+        check(self._h, self._L.sva_kernel_launches(self._h, C.byref(n)))
+        return n.value
+
+    def _shape(self):
+        p = self.params
+        return (p.height, p.width, p.num_disp)
+
+    def download_ad(self):
+        out = np.empty(self._shape(), np.uint16)
+        check(self._h, self._L.sva_frame_download_ad(self._h, _p(out, C.c_uint16)))
+        return out
+
+    def download_cost(self):
+        out = np.empty(self._shape(), np.uint16)
+        check(self._h, self._L.sva_frame_download_cost(self._h, _p(out, C.c_uint16)))
+        return out
+
+    def download_raw_cost(self):
+        out = np.empty(self._shape(), np.uint32)
+        check(self._h, self._L.sva_frame_download_raw_cost(self._h, _p(out, C.c_uint32)))
+        return out
+
+    def download_sgm(self):
+        out = np.empty(self._shape(), np.uint16)
+        check(self._h, self._L.sva_frame_download_sgm(self._h, _p(out, C.c_uint16)))
+        return out
+
+    def download_disparity(self, disp=None, sub=None):
+        p = self.params
+        disp = np.empty((p.height, p.width), np.uint16) if disp is None else disp
+        sub = np.empty((p.height, p.width), np.float32) if sub is None else sub
+        check(self._h, self._L.sva_frame_download_disparity(self._h, _p(disp, C.c_uint16), _p(sub, C.c_float)))
+        return disp, sub
+
+    def ad_device_ptr(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check(self._h, self._L.sva_frame_ad_device_ptr(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def mark_ad_ready(self):
+        check(self._h, self._L.sva_frame_mark_ad_ready(self._h))
+
+    # ---- one call, host in / host out (the e2e path) ----
+    def depth_from_array(self, p, ref, others, mask=None, disp=None, sub=None):
+        r, rk = abi.image_u8(ref)
+        o, ok = abi.image_array(others) if not isinstance(others, tuple) else others
+        m = None
+        if mask is not None:
+            m, mk = abi.image_u8(mask)
+        disp = np.empty((p.height, p.width), np.uint16) if disp is None else disp
+        sub = np.empty((p.height, p.width), np.float32) if sub is None else sub
+        check(self._h, self._L.sva_depth_from_array(self._h, C.byref(p), C.byref(r), o, C.byref(m) if m is not None else None,
+                                                     _p(disp, C.c_uint16), _p(sub, C.c_float)))
+        self.params = p
+        return disp, sub

@@ -1,0 +1,102 @@
+"""CUDA volume pipeline vs the CPU oracle, bit-exact, through the C ABI (libsva_b200.so).  Needs a B200: -m gpu."""
+import numpy as np
+import pytest
+
+from stereovisionarray_b200 import abi, synth
+
+pytestmark = pytest.mark.gpu
+
+OFF8 = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
+OFF15 = [(gx, gy) for gy in range(-1, 3) for gx in range(-1, 3) if (gx, gy) != (0, 0)]
+
+
+@pytest.fixture(scope="module")
+def ctx():
+    from stereovisionarray_b200.pipeline import DepthContext
+    c = DepthContext(0)
+    yield c
+    c.close()
+
+
+CASES = [
+    # h, w, D, offsets, kwargs
+    (64, 96, 64, [(-1, 0)], dict(win_half=4, n_paths=4, lr_gx=-1)),
+    (72, 100, 128, OFF8, dict(win_half=5, n_paths=8, lr_gx=-1)),
+    (70, 90, 192, OFF8, dict(win_half=3, n_paths=8, lr_gx=1)),
+    (66, 120, 256, [(-1, 0), (1, 0)], dict(win_half=6, n_paths=8, lr_gx=-1, min_disp=3)),
+    (60, 88, 32, OFF15, dict(win_half=20, n_paths=8, lr_gx=0)),
+    (61, 83, 16, [(0, -1), (2, 1)], dict(win_half=2, n_paths=4, lr_gx=-1, subpixel=0)),
+    (50, 70, 96, [(-1, 0), (0, 1)], dict(win_half=13, n_paths=0, lr_gx=-1)),
+]
+
+
+@pytest.mark.parametrize("case", range(len(CASES)))
+def test_stages_bit_exact(ctx, oracle, case):
+    h, w, D, offsets, kw = CASES[case]
+    sc = synth.make_scene(h, w, D, offsets, 100 + case, min_disp=kw.get("min_disp", 0), face=(case % 2 == 1))
+    p = abi.make_params(w, h, D, offsets, **kw)
+    ctx.set_debug(0, 0)
+    ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+    ctx.run(abi.STAGE_AD)
+    A = ctx.download_ad()
+    A_o = oracle.ad_volume(p, sc["ref"], sc["others"])
+    assert np.array_equal(A, A_o), "AD volume"
+    ctx.run(abi.STAGE_BOX)
+    Cg = ctx.download_cost()
+    C_o, C32_o = oracle.box_cost(p, A_o, raw=True)
+    assert np.array_equal(Cg, C_o), "packed cost"
+    assert np.array_equal(ctx.download_raw_cost(), C32_o), "raw cost"
+    # every single SGM direction on its own, then the full aggregation (debug: last pass also stores S_total)
+    if p.n_paths:
+        for di in range(p.n_paths):
+            ctx.set_debug(0, 1 << di)
+            ctx.run(abi.STAGE_SGM)
+            assert np.array_equal(ctx.download_sgm(), oracle.sgm_single_path(p, C_o, di)), "direction %d" % di
+    ctx.set_debug(1, 0)
+    ctx.run(abi.STAGE_SGM)
+    S_o = oracle.sgm_aggregate(p, C_o) if p.n_paths else C_o
+    assert np.array_equal(ctx.download_sgm(), S_o), "S total"
+    disp, sub = ctx.download_disparity()
+    disp_o, sub_o = oracle.wta(p, S_o, sc["mask"])
+    assert np.array_equal(disp, disp_o), "integer disparity"
+    assert (disp != abi.SVA_DISP_INVALID).sum() > 0 or case == 4
+    assert np.max(np.abs(sub - sub_o)) <= 0.05  # stated tolerance (north_star); in practice bit-equal
+    assert np.array_equal(sub, sub_o)
+    ctx.set_debug(0, 0)
+
+
+def test_one_call_matches_oracle_pipeline(ctx, oracle):
+    h, w, D = 96, 128, 64
+    sc = synth.make_scene(h, w, D, OFF8, 7)
+    p = abi.make_params(w, h, D, OFF8, win_half=4, n_paths=8, lr_gx=-1)
+    disp, sub = ctx.depth_from_array(p, sc["ref"], sc["others"])
+    disp_o, sub_o = oracle.depth_from_array(p, sc["ref"], sc["others"])
+    assert np.array_equal(disp, disp_o) and np.array_equal(sub, sub_o)
+    assert ctx.launches() > 0
+
+
+def test_pair_range_partials_sum_to_full(ctx, oracle):
+    """what the pair-sharded multi-GPU reduce relies on: AD partials over disjoint pair ranges add up exactly"""
+    h, w, D = 48, 64, 32
+    sc = synth.make_scene(h, w, D, OFF15, 9)
+    p = abi.make_params(w, h, D, OFF15, win_half=4)
+    ctx.upload(p, sc["ref"], sc["others"])
+    tot = np.zeros((h, w, D), np.uint32)
+    for b, e in [(0, 2), (2, 4), (4, 6), (6, 8), (8, 10), (10, 12), (12, 14), (14, 15)]:
+        ctx.set_pair_range(b, e)
+        ctx.run(abi.STAGE_AD)
+        part = ctx.download_ad()
+        assert np.array_equal(part, oracle.ad_volume(p, sc["ref"], sc["others"], b, e))
+        tot += part
+    assert np.array_equal(tot, oracle.ad_volume(p, sc["ref"], sc["others"]))
+
+
+def test_bad_arguments_fail_loudly(ctx):
+    from stereovisionarray_b200._lib import SvaError
+    sc = synth.make_scene(32, 40, 16, [(-1, 0)], 3)
+    p = abi.make_params(40, 32, 20, [(-1, 0)], win_half=2)  # D not a multiple of 8
+    with pytest.raises(SvaError):
+        ctx.upload(p, sc["ref"], sc["others"])
+    p = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2)
+    with pytest.raises(SvaError):
+        ctx.upload(p, sc["ref"][:, :30], sc["others"])  # wrong size
