@@ -209,6 +209,14 @@ inline MatSubExpr operator-(const Mat& a, const Mat& b) {
 }
 inline Mat abs(const MatSubExpr& e) {  // folds to absdiff()
     Mat r(e.a.rows, e.a.cols, e.a.type());
+    if (e.a.type() == CV_8U) {  // the hot call (getAbsDiff): a tight row loop the compiler vectorises, like OpenCV's SIMD absdiff
+        for (int y = 0; y < r.rows; y++) {
+            const uchar* pa = e.a.data + (size_t)y * e.a.step; const uchar* pb = e.b.data + (size_t)y * e.b.step;
+            uchar* pr = r.data + (size_t)y * r.step;
+            for (int x = 0; x < r.cols; x++) pr[x] = pa[x] > pb[x] ? (uchar)(pa[x] - pb[x]) : (uchar)(pb[x] - pa[x]);
+        }
+        return r;
+    }
     for (int y = 0; y < r.rows; y++)
         for (int x = 0; x < r.cols; x++) r.put(y, x, std::fabs(e.a.get(y, x) - e.b.get(y, x)));
     return r;
@@ -226,6 +234,16 @@ inline Mat operator/(double s, const Mat& m) {  // IEEE division for floating ty
     return r;
 }
 inline Scalar sum(const Mat& m) {
+    if (m.type() == CV_8U) {  // exact integer total (OpenCV accumulates u8 in integers, then converts)
+        unsigned long long t = 0;
+        for (int y = 0; y < m.rows; y++) {
+            const uchar* p = m.data + (size_t)y * m.step;
+            unsigned int rs = 0;
+            for (int x = 0; x < m.cols; x++) rs += p[x];
+            t += rs;
+        }
+        return Scalar((double)t);
+    }
     double s = 0;
     for (int y = 0; y < m.rows; y++)
         for (int x = 0; x < m.cols; x++) s += m.get(y, x);

@@ -33,17 +33,29 @@ __device__ __forceinline__ int axis_limit(int pos, int dim, int k, int gp, int g
     return lim;
 }
 
+#define BOX_STAGES 4
+
+// 16-byte async copy global -> shared; src_bytes == 0 zero-fills (out-of-image rows / columns / disparities)
+__device__ __forceinline__ void box_cp16(uint32_t dst, const void* src, int src_bytes) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst), "l"(src), "r"(src_bytes) : "memory");
+}
+
 template <int NC, bool RAW>
 __global__ void __launch_bounds__(BOX_THREADS)
 k_box_cost(BoxParams q) {
     constexpr int TXI = BOX_CG * NC;
-    __shared__ uint2 s_P[TXI][BOX_DP];
-    __shared__ uint2 s_tot[BOX_CG][BOX_DP];
-    __shared__ int s_limy[BOX_MAX_BAND];
+    constexpr int ROW_BYTES = TXI * 64;                 // one tile row: TXI columns x 32 disparities x u16
+    constexpr int STAGE_BYTES = 2 * ROW_BYTES;          // [entering row][leaving row]
+    extern __shared__ __align__(16) unsigned char box_smem[];
+    unsigned char* s_ring = box_smem;                                         // BOX_STAGES * STAGE_BYTES
+    uint2 (*s_P)[BOX_DP] = reinterpret_cast<uint2 (*)[BOX_DP]>(box_smem + BOX_STAGES * STAGE_BYTES);      // [TXI][BOX_DP]
+    uint2 (*s_tot)[BOX_DP] = reinterpret_cast<uint2 (*)[BOX_DP]>(box_smem + BOX_STAGES * STAGE_BYTES + TXI * BOX_DP * 8);  // [BOX_CG][BOX_DP]
+    int* s_limy = reinterpret_cast<int*>(box_smem + BOX_STAGES * STAGE_BYTES + TXI * BOX_DP * 8 + BOX_CG * BOX_DP * 8);
 
     const int t = threadIdx.x, dp = t & (BOX_DP - 1), cg = t >> 4;
     const int W = q.W, H = q.H, D = q.D, k = q.k;
-    const int d = blockIdx.y * 32 + 2 * dp;
+    const int d0 = blockIdx.y * 32;
+    const int d = d0 + 2 * dp;
     const bool d_ok = d < D;
     const int xs = blockIdx.x * q.txo - k;  // global x of strip column 0
     const int y0 = blockIdx.z * q.band_rows, y1 = min(H, y0 + q.band_rows);
@@ -52,35 +64,49 @@ k_box_cost(BoxParams q) {
     for (int i = t; i < y1 - y0; i += BOX_THREADS) s_limy[i] = q.apply_validity ? axis_limit(y0 + i, H, k, q.gyp, q.gyn) : 0x7FFFFFFF;
 
     int limx[NC];
-    bool col_in[NC];
     uint32_t v0[NC], v1[NC];
 #pragma unroll
     for (int j = 0; j < NC; j++) {
         int x = xs + cg * NC + j;
-        col_in[j] = d_ok && x >= 0 && x < W;
         limx[j] = q.apply_validity ? axis_limit(x, W, k, q.gxp, q.gxn) : 0x7FFFFFFF;
         v0[j] = 0; v1[j] = 0;
     }
-    const uint16_t* Acol = q.A + ((long long)(xs + cg * NC)) * D + d;  // + r*W*D + j*D
     const long long rowstride = (long long)W * D;
+    const uint32_t ring_base = (uint32_t)__cvta_generic_to_shared(s_ring);
 
-    auto add_row = [&](int r, bool sub) {
-        if (r < 0 || r >= H) return;
-        uint32_t w[NC];
+    // cooperative stage fill: the tile row is TXI * 4 chunks of 16 B (8 disparities); thread t copies chunks t, t + 256, ...
+    auto fill = [&](int it) {  // iteration it: entering row y0 + it + k - 1, leaving row y0 + it - k (only once it >= 0)
+        const uint32_t st = ring_base + ((it + 2 * k) % BOX_STAGES) * STAGE_BYTES;
+        const int ra = y0 + it + k - 1, rs = y0 + it - k;
+        const bool ra_ok = ra >= 0 && ra < H, rs_ok = it >= 0 && rs >= 0 && rs < H;
 #pragma unroll
-        for (int j = 0; j < NC; j++) w[j] = col_in[j] ? ldg_stream_u32(Acol + r * rowstride + (long long)j * D) : 0u;
-#pragma unroll
-        for (int j = 0; j < NC; j++) {
-            if (sub) { v0[j] -= w[j] & 0xFFFFu; v1[j] -= w[j] >> 16; }
-            else     { v0[j] += w[j] & 0xFFFFu; v1[j] += w[j] >> 16; }
+        for (int c = t; c < TXI * 4; c += BOX_THREADS) {
+            const int col = c >> 2, part = c & 3, x = xs + col, dd = d0 + 8 * part;
+            const bool in = x >= 0 && x < W && dd < D;
+            const long long off = ((long long)(in ? x : 0)) * D + (in ? dd : 0);
+            box_cp16(st + c * 16, q.A + (ra_ok ? ra : 0) * rowstride + off, (in && ra_ok) ? 16 : 0);
+            if (it >= 0) box_cp16(st + ROW_BYTES + c * 16, q.A + (rs_ok ? rs : 0) * rowstride + off, (in && rs_ok) ? 16 : 0);
         }
     };
 
-    for (int r = y0 - k; r <= y0 + k - 2; r++) add_row(r, false);
-    __syncthreads();
+    const int it_begin = -(2 * k - 1), it_end = y1 - y0;  // warm-up iterations (it < 0) only accumulate
+#pragma unroll
+    for (int i = 0; i < BOX_STAGES - 1; i++) {
+        if (it_begin + i < it_end) fill(it_begin + i);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+    }
 
-    for (int y = y0; y < y1; y++) {
-        add_row(y + k - 1, false);
+    for (int it = it_begin; it < it_end; it++) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(BOX_STAGES - 2) : "memory");
+        __syncthreads();  // stage `it` is complete for every thread; everyone has finished reading stage it-1
+        if (it + BOX_STAGES - 1 < it_end) fill(it + BOX_STAGES - 1);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        const unsigned char* st = s_ring + ((it + 2 * k) % BOX_STAGES) * STAGE_BYTES;
+        const uint32_t* rowa = reinterpret_cast<const uint32_t*>(st) + (cg * NC) * 16 + dp;  // [col][16 u32]
+#pragma unroll
+        for (int j = 0; j < NC; j++) { uint32_t w = rowa[j * 16]; v0[j] += w & 0xFFFFu; v1[j] += w >> 16; }
+        if (it < 0) continue;
+        const int y = y0 + it;
         // prefix over this thread's columns
         uint32_t p0[NC], p1[NC];
         uint32_t a0 = 0, a1 = 0;
@@ -93,7 +119,7 @@ k_box_cost(BoxParams q) {
 #pragma unroll
         for (int j = 0; j < NC; j++) s_P[cg * NC + j][dp] = make_uint2(p0[j] + o0, p1[j] + o1);
         __syncthreads();
-        const int limy = s_limy[y - y0];
+        const int limy = s_limy[it];
 #pragma unroll
         for (int j = 0; j < NC; j++) {
             int ci = cg * NC + j, x = xs + ci;
@@ -112,13 +138,26 @@ k_box_cost(BoxParams q) {
                 *reinterpret_cast<uint32_t*>((uint16_t*)q.out + o) = c0 | (c1 << 16);
             }
         }
-        add_row(y - k, true);
+        const uint32_t* rows = reinterpret_cast<const uint32_t*>(st + ROW_BYTES) + (cg * NC) * 16 + dp;
+#pragma unroll
+        for (int j = 0; j < NC; j++) { uint32_t w = rows[j * 16]; v0[j] -= w & 0xFFFFu; v1[j] -= w >> 16; }
     }
 }
 
-// A -> out (u16 packed or u32 raw).  D must be even.  Used by the volume pipeline and (raw, no validity) by literal mode / refine.
+template <int NC, bool RAW>
+static cudaError_t box_launch(const BoxParams& q, dim3 grid, cudaStream_t stream) {
+    constexpr int TXI = BOX_CG * NC;
+    const size_t smem = (size_t)BOX_STAGES * 2 * TXI * 64 + (size_t)TXI * BOX_DP * 8 + BOX_CG * BOX_DP * 8 + BOX_MAX_BAND * 4;
+    cudaError_t e = cudaFuncSetAttribute(k_box_cost<NC, RAW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    k_box_cost<NC, RAW><<<grid, BOX_THREADS, smem, stream>>>(q);
+    return cudaGetLastError();
+}
+
+// A -> out (u16 packed or u32 raw).  D must be a multiple of 8 (16-byte async copies).  Used by the volume pipeline and (raw, no validity) by literal mode / refine.
 int sva_launch_box(sva_ctx* ctx, const uint16_t* A, void* out, int W, int H, int D, int k, const sva_params* prm, bool raw, bool apply_validity) {
     if (k < 1 || k > 56) return ctx->fail(SVA_ERR_BAD_ARG, "win_half must be in 1..56");
+    if (D % 8) return ctx->fail(SVA_ERR_BAD_ARG, "box filter needs a multiple of 8 planes");
     BoxParams q{};
     q.A = A; q.out = out; q.W = W; q.H = H; q.D = D; q.k = k;
     q.dmin = prm ? prm->min_disp : 0; q.shift = prm ? prm->cost_shift : 0; q.cap = prm ? prm->cost_cap : SVA_COST_CAP_MAX;
@@ -146,14 +185,10 @@ int sva_launch_box(sva_ctx* ctx, const uint16_t* A, void* out, int W, int H, int
     bands = div_up(H, q.band_rows);
     dim3 grid(strips, dch, bands);
     LaunchScope ls(ctx, raw ? "k_box_cost_raw" : "k_box_cost");
-    if (wide) {
-        if (raw) k_box_cost<8, true><<<grid, BOX_THREADS, 0, ctx->stream>>>(q);
-        else k_box_cost<8, false><<<grid, BOX_THREADS, 0, ctx->stream>>>(q);
-    } else {
-        if (raw) k_box_cost<4, true><<<grid, BOX_THREADS, 0, ctx->stream>>>(q);
-        else k_box_cost<4, false><<<grid, BOX_THREADS, 0, ctx->stream>>>(q);
-    }
-    SVA_CUDA_OK(ctx, cudaGetLastError());
+    cudaError_t e;
+    if (wide) e = raw ? box_launch<8, true>(q, grid, ctx->stream) : box_launch<8, false>(q, grid, ctx->stream);
+    else e = raw ? box_launch<4, true>(q, grid, ctx->stream) : box_launch<4, false>(q, grid, ctx->stream);
+    SVA_CUDA_OK(ctx, e);
     return SVA_OK;
 }
 

@@ -33,8 +33,8 @@ __global__ void k_shift_perspective(const uint8_t* __restrict__ disp, const uint
 }
 
 // ---- K4: improveWithDisparity — reference src/functions.cpp:11-52 ----------------------------------------------------
-// plane p in [0, 11): |center(y,x) - shifted(y + diry*(p-5), x + dirx*(p-5))|   (u16 [H][W][12], plane 11 = padding)
-#define REFINE_PLANES 12
+// plane p in [0, 11): |center(y,x) - shifted(y + diry*(p-5), x + dirx*(p-5))|   (u16 [H][W][16], planes 11..15 = zero padding)
+#define REFINE_PLANES 16   // 11 used; a multiple of 8 for the box filter's 16-byte copies
 __global__ void k_refine_planes(const uint8_t* __restrict__ center, const uint8_t* __restrict__ shifted, int W, int H, int dirx, int diry,
                                 uint16_t* __restrict__ A) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;

@@ -19,9 +19,11 @@
 // systolic diagonal minimum: one key register per disparity slot shifts by one slot per step (one shuffle per step), so
 // D_o(x') = argmin_d S(y, x'+lr_gx*delta, d) falls out of the same march with no extra memory traffic.  Results of a row
 // are staged in shared memory and written coalesced by a row-end sweep that applies mask / border / cell-validity / LR.
+#include <algorithm>
+
 #include "sva_common.cuh"
 
-#define SGM_PF 8
+// PF = steps of prefetch in flight per warp; the ring has PF + 1 stages (the slot refilled at step s was last read at step s-1)
 #define SGM_INF2 0x7FFF7FFFu
 #define SGM_WARPS 8
 #define SGM_FINAL_WARPS 4
@@ -32,15 +34,21 @@ struct SgmParams {
     const uint16_t* C;
     uint16_t* S;
     int W, H, D;
-    int dx, dy;
+    int ndirs;          // directions processed concurrently by this launch: CTA b handles direction b % ndirs
+    int dxs[8], dys[8];
     uint32_t p1p1, p2p2;
     int lanes;  // active lanes = D / (2*NR)
     // final pass only
     int dmin, k, gxp, gxn, gyp, gyn, lr_gx, lr_max_diff, subpixel, store_full, no_agg;
+    int wta_only;       // the march only reads S_total (all paths already accumulated) and does K3
     const uint8_t* mask;
     uint16_t* disp;
     float* sub;
 };
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 template <int NR> struct Vec;
 template <> struct Vec<1> {
@@ -48,6 +56,8 @@ template <> struct Vec<1> {
     static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[1]) {
         asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
     }
+    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(p) : "memory"); }
+    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[1]) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[0]) : "r"(src)); }
     static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[1]) { *reinterpret_cast<uint32_t*>(p) = r[0]; }
     static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[1]) {
         asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(r[0]) : "memory");
@@ -58,6 +68,8 @@ template <> struct Vec<2> {
     static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[2]) {
         asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
     }
+    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p) : "memory"); }
+    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[2]) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(src)); }
     static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[2]) { *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]); }
     static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[2]) {
         unsigned long long v = ((unsigned long long)r[1] << 32) | r[0];
@@ -69,6 +81,8 @@ template <> struct Vec<4> {
     static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[4]) {
         asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
     }
+    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p) : "memory"); }
+    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[4]) { asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(src)); }
     static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[4]) { *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]); }
     static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[4]) {
         unsigned long long v0 = ((unsigned long long)r[1] << 32) | r[0], v1 = ((unsigned long long)r[3] << 32) | r[2];
@@ -105,18 +119,22 @@ __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)
     mp2 = mm + p2p2;
 }
 
+int sva_run_wta(sva_ctx* ctx, const uint16_t* vol);
+
 struct PathPos {
     int x, y;
 };
 
-template <int NR, int MODE>
+template <int NR, int MODE, int SGM_PF>
 __global__ void __launch_bounds__(MODE == SGM_MODE_FINAL ? SGM_FINAL_WARPS * 32 : SGM_WARPS * 32)
 k_sgm_pass(SgmParams q) {
+    constexpr int SGM_NS = SGM_PF + 1;
     constexpr int NV = 2 * NR;
     constexpr int WARPS = MODE == SGM_MODE_FINAL ? SGM_FINAL_WARPS : SGM_WARPS;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int line = blockIdx.x * WARPS + warp;
-    const int W = q.W, H = q.H, D = q.D, dx = q.dx, dy = q.dy;
+    const int dir = blockIdx.x % q.ndirs;
+    const int line = (blockIdx.x / q.ndirs) * WARPS + warp;
+    const int W = q.W, H = q.H, D = q.D, dx = q.dxs[dir], dy = q.dys[dir];
     const int nlines = dy == 0 ? H : W, len = dy == 0 ? W : H;
     if (line >= nlines) return;
     const bool active = lane < q.lanes;
@@ -138,18 +156,26 @@ k_sgm_pass(SgmParams q) {
         return false;
     };
 
-    uint32_t cbuf[SGM_PF][NR], sbuf[MODE == SGM_MODE_FINAL ? SGM_PF : 1][NR];
+    // ---- streaming: cp.async (LDGSTS) into a per-warp ring of SGM_NS stages; wait_group gives FIFO completion, which the
+    // register scoreboard cannot (a register prefetch ring deeper than the scoreboard slots serialises on DRAM latency) ----
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int STAGE_BYTES = 32 * NV * 2;                         // one step of one volume for the whole warp
+    constexpr int NVOL = MODE == SGM_MODE_FINAL ? 2 : 1;             // final pass streams C and S
+    constexpr int RING_BYTES = SGM_NS * NVOL * STAGE_BYTES;
+    const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (NV * 2);
+    const bool wta_only = MODE == SGM_MODE_FINAL && q.wta_only;
+    const bool stream_s = MODE == SGM_MODE_FINAL && !q.no_agg && !wta_only;
+    const uint16_t* vol0 = wta_only ? q.S : q.C;
+    auto issue = [&](int slot) {  // loads for the cell under the prefetch cursor into ring slot `slot`
+        if (active) {
+            Vec<NR>::cp_async(ring + slot * NVOL * STAGE_BYTES, vol0 + cell(pre));
+            if (stream_s) Vec<NR>::cp_async(ring + slot * NVOL * STAGE_BYTES + STAGE_BYTES, q.S + cell(pre));
+        }
+    };
 #pragma unroll
     for (int u = 0; u < SGM_PF; u++) {
-#pragma unroll
-        for (int j = 0; j < NR; j++) { cbuf[u][j] = SGM_INF2; if (MODE == SGM_MODE_FINAL) sbuf[u][j] = 0; }
-        if (u < len) {
-            if (active) {
-                Vec<NR>::load(q.C + cell(pre), cbuf[u]);
-                if (MODE == SGM_MODE_FINAL && !q.no_agg) Vec<NR>::load_rw(q.S + cell(pre), sbuf[u]);
-            }
-            advance(pre);
-        }
+        if (u < len) { issue(u); advance(pre); }
+        cp_async_commit();
     }
 
     uint32_t L[NR];
@@ -159,12 +185,11 @@ k_sgm_pass(SgmParams q) {
     bool restart = true;
 
     // ---- final-pass state ----
-    extern __shared__ unsigned char smem_raw[];
     uint16_t* pend_d = nullptr; float* pend_sub = nullptr; uint16_t* other_row = nullptr;
     uint32_t acc[NV];
     const int tdir = q.lr_gx * dx;  // +1: LR entries travel towards larger d; -1: towards smaller d
     if (MODE == SGM_MODE_FINAL) {
-        unsigned char* base = smem_raw + (size_t)warp * (8 * (size_t)W);
+        unsigned char* base = smem_raw + WARPS * RING_BYTES + (size_t)warp * (8 * (size_t)W);
         pend_sub = reinterpret_cast<float*>(base);
         pend_d = reinterpret_cast<uint16_t*>(base + 4 * (size_t)W);
         other_row = reinterpret_cast<uint16_t*>(base + 6 * (size_t)W);
@@ -174,27 +199,28 @@ k_sgm_pass(SgmParams q) {
         __syncwarp();
     }
 
-    for (int s0 = 0; s0 < len; s0 += SGM_PF) {
+    for (int s0 = 0; s0 < len; s0 += SGM_NS) {
 #pragma unroll
-        for (int u = 0; u < SGM_PF; u++) {
-            const int s = s0 + u;
+        for (int u = 0; u < SGM_NS; u++) {
+            const int s = s0 + u;   // step s lives in ring slot s % SGM_NS == u
             if (s >= len) break;
+            cp_async_wait<SGM_PF - 1>();
             uint32_t Cc[NR], Sp[NR];
 #pragma unroll
-            for (int j = 0; j < NR; j++) { Cc[j] = cbuf[u][j]; if (MODE == SGM_MODE_FINAL) Sp[j] = sbuf[u][j]; }
-            if (s + SGM_PF < len) {
-                if (active) {
-                    Vec<NR>::load(q.C + cell(pre), cbuf[u]);
-                    if (MODE == SGM_MODE_FINAL && !q.no_agg) Vec<NR>::load_rw(q.S + cell(pre), sbuf[u]);
-                }
-                advance(pre);
+            for (int j = 0; j < NR; j++) { Cc[j] = SGM_INF2; Sp[j] = 0; }
+            if (active) {
+                Vec<NR>::lds(ring + u * NVOL * STAGE_BYTES, Cc);
+                if (stream_s) Vec<NR>::lds(ring + u * NVOL * STAGE_BYTES + STAGE_BYTES, Sp);
             }
+            // refill the slot that was consumed one step ago with step s + PF
+            if (s + SGM_PF < len) { issue((u + SGM_PF) % SGM_NS); advance(pre); }
+            cp_async_commit();
             if (restart || (MODE == SGM_MODE_FINAL && q.no_agg)) {
 #pragma unroll
                 for (int j = 0; j < NR; j++) L[j] = 0;
                 mm = 0; mp2 = q.p2p2;
             }
-            sgm_step<NR>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+            if (!wta_only) sgm_step<NR>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
 
             if (MODE == SGM_MODE_STORE) {
                 if (active) Vec<NR>::store(q.S + cell(pos), L);
@@ -204,8 +230,8 @@ k_sgm_pass(SgmParams q) {
                 // ---- fused K3 ----
                 uint32_t St[NR];
 #pragma unroll
-                for (int j = 0; j < NR; j++) St[j] = q.no_agg ? L[j] : Sp[j] + L[j];
-                if (q.store_full && active) Vec<NR>::store(q.S + cell(pos), St);
+                for (int j = 0; j < NR; j++) St[j] = wta_only ? Cc[j] : (q.no_agg ? L[j] : Sp[j] + L[j]);
+                if (q.store_full && !wta_only && active) Vec<NR>::store(q.S + cell(pos), St);
                 uint32_t key[NV];
                 uint32_t kbest = 0xFFFFFFFFu;
 #pragma unroll
@@ -305,31 +331,128 @@ k_sgm_pass(SgmParams q) {
     }
 }
 
-template <int NR>
+// ---- lean accumulate march (the hot kernel): same recurrence and ring as above, specialised at compile time on
+// DIAG (wrap/restart logic only for diagonals), FULL (all 32 lanes active: no predicates) and STORE (plain store vs RED),
+// running 64-bit cursors instead of recomputed cell indices, and an unchecked steady-state loop with a checked tail.
+template <int NR, int PF, bool FULL, bool DIAG, bool STORE>
+__device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t ring) {
+    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
+    const int W = q.W, H = q.H, D = q.D;
+    const int len = dy == 0 ? W : H;
+    const int x0 = dy == 0 ? (dx > 0 ? 0 : W - 1) : line, y0 = dy == 0 ? line : (dy > 0 ? 0 : H - 1);
+    const long long dstep = ((long long)dy * W + dx) * D, wrapfix = -(long long)dx * W * D;
+    const long long start = ((long long)y0 * W + x0) * D + lane * NV;
+    const uint16_t* pc = q.C + start;  // prefetch cursor
+    uint16_t* ps = q.S + start;        // accumulate cursor
+    int xc = x0, xs = x0;
+    const bool active = FULL || lane < q.lanes;
+    const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
+    auto adv = [&](auto& p, int& xx) -> bool {
+        p += dstep;
+        if (DIAG) {
+            xx += dx;
+            if (xx >= W) { xx = 0; p += wrapfix; return true; }
+            if (xx < 0) { xx = W - 1; p += wrapfix; return true; }
+        }
+        return false;
+    };
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, pc); adv(pc, xc); }
+        cp_async_commit();
+    }
+    uint32_t L[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) L[j] = 0;
+    uint32_t mm = 0, mp2 = q.p2p2;
+    bool restart = false;  // step 0 starts from L = 0, mm = 0, which yields L = C
+    auto step = [&](const uint32_t slot_addr, const uint32_t refill_addr, const bool refill) {
+        cp_async_wait<PF - 1>();
+        uint32_t Cc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
+        if (active) Vec<NR>::lds(slot_addr, Cc);
+        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, pc); adv(pc, xc); }
+        cp_async_commit();
+        if (DIAG && restart) {
+#pragma unroll
+            for (int j = 0; j < NR; j++) L[j] = 0;
+            mm = 0; mp2 = q.p2p2;
+        }
+        sgm_step<NR>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+        if (active) { if (STORE) Vec<NR>::store(ps, L); else Vec<NR>::red(ps, L); }
+        restart = adv(ps, xs);
+    };
+    int s0 = 0;
+    for (; s0 + NS + PF <= len; s0 += NS) {
+#pragma unroll
+        for (int u = 0; u < NS; u++) step(ring + u * STAGE, ring + ((u + PF) % NS) * STAGE, true);
+    }
+    for (int s = s0; s < len; s++) step(ring + (s % NS) * STAGE, ring + ((s + PF) % NS) * STAGE, s + PF < len);
+}
+
+template <int NR, int PF, bool FULL, bool STORE>
+__global__ void __launch_bounds__(SGM_WARPS * 32)
+k_sgm_acc(SgmParams q) {
+    constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int dir = blockIdx.x % q.ndirs;
+    const int line = (blockIdx.x / q.ndirs) * SGM_WARPS + warp;
+    const int dx = q.dxs[dir], dy = q.dys[dir];
+    if (line >= (dy == 0 ? q.H : q.W)) return;
+    const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (4 * NR);
+    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE>(q, dx, dy, line, lane, ring);
+    else sgm_acc_march<NR, PF, FULL, false, STORE>(q, dx, dy, line, lane, ring);
+}
+
+template <int NR, int PF, bool FULL, bool STORE>
+static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_smem, const char* name) {
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+    LaunchScope ls(ctx, name);
+    k_sgm_acc<NR, PF, FULL, STORE><<<div_up(nlines, SGM_WARPS) * q.ndirs, SGM_WARPS * 32, ring_smem, ctx->stream>>>(q);
+    return SVA_OK;
+}
+
+template <int NR, int PF>
 static int launch_pass(sva_ctx* ctx, const SgmParams& q, int mode) {
-    const int nlines = q.dy == 0 ? q.H : q.W;
+    int nlines = 0;
+    for (int i = 0; i < q.ndirs; i++) nlines = std::max(nlines, q.dys[i] == 0 ? q.H : q.W);
+    const size_t ring_smem = (size_t)SGM_WARPS * (PF + 1) * 32 * 2 * NR * 2;
     if (mode == SGM_MODE_FINAL) {
-        size_t smem = (size_t)SGM_FINAL_WARPS * 8 * q.W;
-        if (smem > 200 * 1024) return ctx->fail(SVA_ERR_BAD_ARG, "image too wide for the fused final pass (W > 6400)");
-        SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_FINAL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        LaunchScope ls(ctx, "k_sgm_final");
-        k_sgm_pass<NR, SGM_MODE_FINAL><<<div_up(nlines, SGM_FINAL_WARPS), SGM_FINAL_WARPS * 32, smem, ctx->stream>>>(q);
+        size_t smem = (size_t)SGM_FINAL_WARPS * 8 * q.W + (size_t)SGM_FINAL_WARPS * (PF + 1) * 2 * 32 * 2 * NR * 2;
+        if (smem > 200 * 1024) return ctx->fail(SVA_ERR_BAD_ARG, "image too wide for the fused final pass");
+        SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_FINAL, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        LaunchScope ls(ctx, q.wta_only ? "k_wta_march" : "k_sgm_final");
+        k_sgm_pass<NR, SGM_MODE_FINAL, PF><<<div_up(nlines, SGM_FINAL_WARPS), SGM_FINAL_WARPS * 32, smem, ctx->stream>>>(q);
+    } else if (ctx->tune_sgm_lean) {
+        const bool full = q.lanes == 32;
+        if (mode == SGM_MODE_STORE) {
+            const char* nm = q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d");
+            SVA_TRY((full ? launch_acc<NR, PF, true, true>(ctx, q, nlines, ring_smem, nm) : launch_acc<NR, PF, false, true>(ctx, q, nlines, ring_smem, nm)));
+        } else {
+            const char* nm = q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d"));
+            SVA_TRY((full ? launch_acc<NR, PF, true, false>(ctx, q, nlines, ring_smem, nm) : launch_acc<NR, PF, false, false>(ctx, q, nlines, ring_smem, nm)));
+        }
     } else if (mode == SGM_MODE_STORE) {
-        LaunchScope ls(ctx, q.dy == 0 ? "k_sgm_store_h" : (q.dx == 0 ? "k_sgm_store_v" : "k_sgm_store_d"));
-        k_sgm_pass<NR, SGM_MODE_STORE><<<div_up(nlines, SGM_WARPS), SGM_WARPS * 32, 0, ctx->stream>>>(q);
+        SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_STORE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        LaunchScope ls(ctx, q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d"));
+        k_sgm_pass<NR, SGM_MODE_STORE, PF><<<div_up(nlines, SGM_WARPS), SGM_WARPS * 32, ring_smem, ctx->stream>>>(q);
     } else {
-        LaunchScope ls(ctx, q.dy == 0 ? "k_sgm_red_h" : (q.dx == 0 ? "k_sgm_red_v" : "k_sgm_red_d"));
-        k_sgm_pass<NR, SGM_MODE_RED><<<div_up(nlines, SGM_WARPS), SGM_WARPS * 32, 0, ctx->stream>>>(q);
+        SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_RED, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+        LaunchScope ls(ctx, q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d")));
+        k_sgm_pass<NR, SGM_MODE_RED, PF><<<div_up(nlines, SGM_WARPS) * q.ndirs, SGM_WARPS * 32, ring_smem, ctx->stream>>>(q);
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     return SVA_OK;
 }
 
 static int launch_pass_nr(sva_ctx* ctx, const SgmParams& q, int nr, int mode) {
+    const int pf = ctx->tune_sgm_pf;
     switch (nr) {
-        case 1: return launch_pass<1>(ctx, q, mode);
-        case 2: return launch_pass<2>(ctx, q, mode);
-        default: return launch_pass<4>(ctx, q, mode);
+        case 1: return pf >= 16 ? launch_pass<1, 16>(ctx, q, mode) : launch_pass<1, 8>(ctx, q, mode);
+        case 2: return pf >= 16 ? launch_pass<2, 16>(ctx, q, mode) : launch_pass<2, 8>(ctx, q, mode);
+        default: return pf >= 16 ? launch_pass<4, 16>(ctx, q, mode) : launch_pass<4, 8>(ctx, q, mode);
     }
 }
 
@@ -372,7 +495,7 @@ int sva_run_sgm(sva_ctx* ctx) {
         bool first = true;
         for (int i = 0; i < 8; i++) {
             if (!(ctx->sgm_dir_mask_override & (1u << i))) continue;
-            q.dx = DIRS[i][0]; q.dy = DIRS[i][1];
+            q.ndirs = 1; q.dxs[0] = DIRS[i][0]; q.dys[0] = DIRS[i][1];
             SVA_TRY(launch_pass_nr(ctx, q, nr, first ? SGM_MODE_STORE : SGM_MODE_RED));
             first = false;
         }
@@ -382,13 +505,49 @@ int sva_run_sgm(sva_ctx* ctx) {
     static const int order8[8] = {0, 1, 4, 5, 6, 7, 2, 3}, order4[4] = {0, 1, 2, 3};
     const int n = p.n_paths;
     const int* order = n == 8 ? order8 : order4;
-    for (int i = 0; i + 1 < n; i++) {
-        q.dx = DIRS[order[i]][0]; q.dy = DIRS[order[i]][1];
-        SVA_TRY(launch_pass_nr(ctx, q, nr, i == 0 ? SGM_MODE_STORE : SGM_MODE_RED));
+    if (ctx->tune_sgm_fused_final) {
+        // variant A: first path stores, middle paths RED (one concurrent launch), last path fused with K3 in one march
+        if (n > 0) {
+            q.ndirs = 1; q.dxs[0] = DIRS[order[0]][0]; q.dys[0] = DIRS[order[0]][1];
+            SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_STORE));
+        }
+        if (ctx->tune_sgm_concurrent && n > 2) {
+            q.ndirs = n - 2;
+            for (int i = 1; i + 1 < n; i++) { q.dxs[i - 1] = DIRS[order[i]][0]; q.dys[i - 1] = DIRS[order[i]][1]; }
+            SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+        } else {
+            for (int i = 1; i + 1 < n; i++) {
+                q.ndirs = 1; q.dxs[0] = DIRS[order[i]][0]; q.dys[0] = DIRS[order[i]][1];
+                SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+            }
+        }
+        q.ndirs = 1; q.dxs[0] = -1; q.dys[0] = 0;
+        q.no_agg = n == 0 ? 1 : 0;
+        SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_FINAL));
+    } else {
+        // variant B (default): S = 0, ALL paths accumulate with REDs in ONE launch (directions interleaved over CTAs: more
+        // memory-level parallelism, and paths sweeping the same rows share C and S lines in L2), then a recurrence-free
+        // horizontal march does K3 (WTA + LR + sub-pixel) on S_total
+        if (n == 0) {  // no aggregation: K3 straight on the cost volume
+            SVA_TRY(sva_run_wta(ctx, ctx->C.as<uint16_t>()));
+            ctx->have_sgm = false; ctx->have_disp = true;
+            return SVA_OK;
+        }
+        SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.p, 0, cells * sizeof(uint16_t), ctx->stream));
+        q.ndirs = n;
+        // interleave so that neighbouring CTAs sweep the same rows: down, down-diagonals, up, up-diagonals, horizontals
+        static const int conc8[8] = {0, 4, 5, 1, 6, 7, 2, 3}, conc4[4] = {0, 1, 2, 3};
+        const int* co = n == 8 ? conc8 : conc4;
+        for (int i = 0; i < n; i++) { q.dxs[i] = DIRS[co[i]][0]; q.dys[i] = DIRS[co[i]][1]; }
+        SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+        if (ctx->tune_wta_march) {  // K3 as a recurrence-free horizontal march (kept for comparison)
+            q.ndirs = 1; q.dxs[0] = -1; q.dys[0] = 0;
+            q.wta_only = 1;
+            SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_FINAL));
+        } else {
+            SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
+        }
     }
-    q.dx = -1; q.dy = 0;
-    q.no_agg = n == 0 ? 1 : 0;
-    SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_FINAL));
     ctx->have_sgm = true; ctx->have_disp = true;
     return SVA_OK;
 }

@@ -55,6 +55,11 @@ struct sva_ctx {
     int pair_begin = 0, pair_end = 0;
     bool has_mask = false;
     bool debug_store_full_s = false;
+    int tune_sgm_pf = 8;          // SVA_SGM_PF: cp.async prefetch depth of the SGM passes (8 or 16)
+    int tune_sgm_concurrent = 1;  // SVA_SGM_CONCURRENT: run the RED-accumulating SGM directions in one launch
+    int tune_sgm_fused_final = 0; // SVA_SGM_FUSED_FINAL: last path + K3 in one march (variant A) instead of all-RED + WTA march
+    int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
+    int tune_wta_march = 0;       // SVA_WTA_MARCH: K3 as a warp-per-row march instead of the tile kernel
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, C, Craw, S, disp, subpix, other_d, scratch, scratch2;

@@ -1,5 +1,6 @@
 // sva_ctx.cu — context lifetime, HBM workspaces, event-based kernel timing.
 #include <cstdio>
+#include <cstdlib>
 
 #include "sva_common.cuh"
 
@@ -61,6 +62,11 @@ int sva_create(int device, sva_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SVA_ERR_CUDA; }
     c->stream = c->own_stream;
+    if (const char* e = getenv("SVA_SGM_PF")) c->tune_sgm_pf = atoi(e);
+    if (const char* e = getenv("SVA_SGM_CONCURRENT")) c->tune_sgm_concurrent = atoi(e);
+    if (const char* e = getenv("SVA_SGM_FUSED_FINAL")) c->tune_sgm_fused_final = atoi(e);
+    if (const char* e = getenv("SVA_WTA_MARCH")) c->tune_wta_march = atoi(e);
+    if (const char* e = getenv("SVA_SGM_LEAN")) c->tune_sgm_lean = atoi(e);
     *out = c;
     return SVA_OK;
 }

@@ -55,7 +55,8 @@ def test_stages_bit_exact(ctx, oracle, case):
     ctx.set_debug(1, 0)
     ctx.run(abi.STAGE_SGM)
     S_o = oracle.sgm_aggregate(p, C_o) if p.n_paths else C_o
-    assert np.array_equal(ctx.download_sgm(), S_o), "S total"
+    if p.n_paths:
+        assert np.array_equal(ctx.download_sgm(), S_o), "S total"
     disp, sub = ctx.download_disparity()
     disp_o, sub_o = oracle.wta(p, S_o, sc["mask"])
     assert np.array_equal(disp, disp_o), "integer disparity"
