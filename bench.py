@@ -73,7 +73,7 @@ class ClockSampler:
         return out
 
 
-def algorithmic_bytes(name, p, n_cam):
+def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
     """per launch, DESIGN.md §4: s_C = s_S = 2 bytes"""
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
@@ -84,7 +84,8 @@ def algorithmic_bytes(name, p, n_cam):
     if name.startswith("k_sgm_store"):
         return 4 * de
     if name == "k_sgm_red_multi":  # launches_per_step tells which variant ran; bytes are per launch
-        return 6 * de * (p.n_paths - 2 if os.environ.get("SVA_SGM_FUSED_FINAL", "0") == "1" else p.n_paths)
+        dirs = p.n_paths - 2 if os.environ.get("SVA_SGM_FUSED_FINAL", "0") == "1" else p.n_paths
+        return 6 * de * dirs / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
     if name in ("k_wta_march", "k_wta_tile"):
         return 2 * de + 6 * px
     if name == "k_lr_check":
@@ -180,7 +181,7 @@ def run_sva(args):
         pass
     rows = []
     for kname, (sum_ms, cnt) in kern.items():
-        ab = algorithmic_bytes(kname, p, n_cam)
+        ab = algorithmic_bytes(kname, p, n_cam, cnt / args.steps)
         avg_ms = sum_ms / max(1, cnt)
         rows.append({"kernel": kname, "launches_per_step": cnt / args.steps, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
                      "algorithmic_bytes": ab, "achieved_gbs": round(ab / avg_ms / 1e6, 1) if ab else None,

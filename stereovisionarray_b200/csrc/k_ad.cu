@@ -35,52 +35,68 @@ __device__ __forceinline__ void ad_accumulate(uint32_t diff, uint32_t& even, uin
     odd += __byte_perm(diff, 0, 0x4341);   // cells 1 and 3 as u16x2
 }
 
-// one thread = 8 consecutive disparities of one pixel; 16-byte coalesced store
+// 8 consecutive disparities (bytes) of one pixel's epipolar walk in pair k's line image, starting at byte offset `off`
+__device__ __forceinline__ void ad_gather8(const uint8_t* __restrict__ L, int off, int g, uint32_t& b0, uint32_t& b1) {
+    const uint32_t* wp = (const uint32_t*)(L + (off & ~3));
+    const int sh = (off & 3) * 8;
+    if (g == 1) {
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
+        b0 = __funnelshift_r(w0, w1, sh);
+        b1 = __funnelshift_r(w1, w2, sh);
+    } else if (g == 2) {
+        uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
+        uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
+        uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
+        b0 = __byte_perm(a0, a1, 0x6420);
+        b1 = __byte_perm(a2, a3, 0x6420);
+    } else {  // rare general stride: byte gathers
+        const uint8_t* q = L + off;
+        b0 = q[0] | (q[g] << 8) | (q[2 * g] << 16) | ((uint32_t)q[3 * g] << 24);
+        b1 = q[4 * g] | (q[5 * g] << 8) | (q[6 * g] << 16) | ((uint32_t)q[7 * g] << 24);
+    }
+}
+
+// one thread = CH chunks of 8 disparities of one pixel (CH = 4 when D % 32 == 0: the per-pair setup is amortised over 32 cells).
+// The chunks of a thread are interleaved with those of the other threads of the pixel (chunk = gi + groups*c), so every
+// 16-byte store instruction of a warp writes whole contiguous runs (full 32-byte sectors)
+template <int CH>
 __global__ void __launch_bounds__(256)
 k_ad_volume(const uint8_t* __restrict__ ref, size_t ref_pitch, const uint8_t* __restrict__ lines, AdPairs P, int W, int H, int D,
             int dmin, uint16_t* __restrict__ A) {
-    const int chunks = D >> 3;
+    const int groups = D / (8 * CH);
     long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)W * H * chunks;
+    long long total = (long long)W * H * groups;
     if (tid >= total) return;
-    int c8 = (int)(tid % chunks);
-    long long pix = tid / chunks;
+    int gi = (int)(tid % groups);
+    long long pix = tid / groups;
     int x = (int)(pix % W), y = (int)(pix / W);
-    uint32_t r = ref[(size_t)y * ref_pitch + x];
-    uint32_t r4 = r * 0x01010101u;
-    int delta0 = dmin + 8 * c8;
-    uint32_t e0 = 0, o0 = 0, e1 = 0, o1 = 0;  // (cells 0,2) (1,3) (4,6) (5,7)
+    uint32_t r4 = (uint32_t)ref[(size_t)y * ref_pitch + x] * 0x01010101u;
+    int delta0 = dmin + 8 * gi;
+    uint32_t e0[CH], o0[CH], e1[CH], o1[CH];  // per chunk: (cells 0,2) (1,3) (4,6) (5,7) as u16x2
+#pragma unroll
+    for (int c = 0; c < CH; c++) { e0[c] = 0; o0[c] = 0; e1[c] = 0; o1[c] = 0; }
     for (int k = 0; k < P.n; k++) {
         const uint8_t* L = lines + P.line_off[k];
-        int off = P.base[k] + x * P.alpha[k] + y * P.beta[k] + P.g[k] * delta0;
-        const uint32_t* wp = (const uint32_t*)(L + (off & ~3));
-        int sh = (off & 3) * 8;
-        uint32_t b0, b1;
-        if (P.g[k] == 1) {
-            uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2);
-            b0 = __funnelshift_r(w0, w1, sh);
-            b1 = __funnelshift_r(w1, w2, sh);
-        } else if (P.g[k] == 2) {
-            uint32_t w0 = __ldg(wp), w1 = __ldg(wp + 1), w2 = __ldg(wp + 2), w3 = __ldg(wp + 3), w4 = __ldg(wp + 4);
-            uint32_t a0 = __funnelshift_r(w0, w1, sh), a1 = __funnelshift_r(w1, w2, sh);
-            uint32_t a2 = __funnelshift_r(w2, w3, sh), a3 = __funnelshift_r(w3, w4, sh);
-            b0 = __byte_perm(a0, a1, 0x6420);
-            b1 = __byte_perm(a2, a3, 0x6420);
-        } else {  // rare general stride: byte gathers
-            const uint8_t* q = L + off;
-            int g = P.g[k];
-            b0 = q[0] | (q[g] << 8) | (q[2 * g] << 16) | ((uint32_t)q[3 * g] << 24);
-            b1 = q[4 * g] | (q[5 * g] << 8) | (q[6 * g] << 16) | ((uint32_t)q[7 * g] << 24);
+        const int g = P.g[k];
+        const int off = P.base[k] + x * P.alpha[k] + y * P.beta[k] + g * delta0;
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            uint32_t b0, b1;
+            ad_gather8(L, off + 8 * g * groups * c, g, b0, b1);
+            ad_accumulate(__vabsdiffu4(b0, r4), e0[c], o0[c]);
+            ad_accumulate(__vabsdiffu4(b1, r4), e1[c], o1[c]);
         }
-        ad_accumulate(__vabsdiffu4(b0, r4), e0, o0);
-        ad_accumulate(__vabsdiffu4(b1, r4), e1, o1);
     }
-    uint4 out;
-    out.x = __byte_perm(e0, o0, 0x5410);  // cells 0,1
-    out.y = __byte_perm(e0, o0, 0x7632);  // cells 2,3
-    out.z = __byte_perm(e1, o1, 0x5410);
-    out.w = __byte_perm(e1, o1, 0x7632);
-    *reinterpret_cast<uint4*>(A + ((size_t)pix * D + 8 * c8)) = out;
+    uint4* out = reinterpret_cast<uint4*>(A + ((size_t)pix * D + 8 * gi));
+#pragma unroll
+    for (int c = 0; c < CH; c++) {
+        uint4 v;
+        v.x = __byte_perm(e0[c], o0[c], 0x5410);  // cells 0,1
+        v.y = __byte_perm(e0[c], o0[c], 0x7632);  // cells 2,3
+        v.z = __byte_perm(e1[c], o1[c], 0x5410);
+        v.w = __byte_perm(e1[c], o1[c], 0x7632);
+        out[c * groups] = v;
+    }
 }
 
 static void ext_gcd(int a, int b, int& g, int& u, int& v) {  // u*a + v*b = g >= 0
@@ -144,11 +160,17 @@ int sva_run_ad(sva_ctx* ctx) {
         const PairGeom& G = ctx->geom[ctx->pair_begin + i];
         P.alpha[i] = G.alpha; P.beta[i] = G.beta; P.base[i] = G.base; P.g[i] = G.g; P.line_off[i] = G.offset;
     }
-    long long threads = (long long)W * H * (D / 8);
     {
         LaunchScope ls(ctx, "k_ad_volume");
-        k_ad_volume<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D,
-                                                                              p.min_disp, ctx->A.as<uint16_t>());
+        if (D % 32 == 0) {
+            long long threads = (long long)W * H * (D / 32);
+            k_ad_volume<4><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D,
+                                                                                     p.min_disp, ctx->A.as<uint16_t>());
+        } else {
+            long long threads = (long long)W * H * (D / 8);
+            k_ad_volume<1><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D,
+                                                                                     p.min_disp, ctx->A.as<uint16_t>());
+        }
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     ctx->have_ad = true;

@@ -175,7 +175,7 @@ int sva_launch_box(sva_ctx* ctx, const uint16_t* A, void* out, int W, int H, int
     const int txi = wide ? 128 : 64;
     q.txo = txi - 2 * k + 1;
     int strips = div_up(W, q.txo), dch = div_up(D, 32);
-    // enough CTAs to fill the machine twice over, bands no shorter than 4k rows (warm-up is 2k-1 rows of loads)
+    // enough CTAs for one full wave, bands no shorter than 4k rows (warm-up is 2k-1 rows of loads)
     int bands = div_up(2 * ctx->sm_count * 2, strips * dch);
     int min_band = 4 * k > 32 ? 4 * k : 32;
     if (bands > H / min_band) bands = H / min_band;

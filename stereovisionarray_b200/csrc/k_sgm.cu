@@ -20,6 +20,7 @@
 // D_o(x') = argmin_d S(y, x'+lr_gx*delta, d) falls out of the same march with no extra memory traffic.  Results of a row
 // are staged in shared memory and written coalesced by a row-end sweep that applies mask / border / cell-validity / LR.
 #include <algorithm>
+#include <cstdlib>
 
 #include "sva_common.cuh"
 
@@ -41,6 +42,11 @@ struct SgmParams {
     // final pass only
     int dmin, k, gxp, gxn, gyp, gyn, lr_gx, lr_max_diff, subpixel, store_full, no_agg;
     int wta_only;       // the march only reads S_total (all paths already accumulated) and does K3
+    unsigned int* pace_arrive;  // k_sgm_acc: [pace_rounds] CTAs that finished round r (nullptr = no global pacing)
+    unsigned int* pace_min;     // rounds finished by every CTA
+    int pace_rounds, pace_window, march_warps;
+    int cta_sync;       // k_sgm_acc (balanced): named barrier among the row-sweeping warps of a CTA every round
+    int balanced;       // k_sgm_acc: grid = m * SM count; warp w of CTA b handles direction w % ndirs, line b + grid * (w / ndirs)
     const uint8_t* mask;
     uint16_t* disp;
     float* sub;
@@ -335,7 +341,8 @@ k_sgm_pass(SgmParams q) {
 // DIAG (wrap/restart logic only for diagonals), FULL (all 32 lanes active: no predicates) and STORE (plain store vs RED),
 // running 64-bit cursors instead of recomputed cell indices, and an unchecked steady-state loop with a checked tail.
 template <int NR, int PF, bool FULL, bool DIAG, bool STORE>
-__device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t ring) {
+__device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t ring, const int bar_threads,
+                                              volatile int* s_pace /* [0] rounds finished by this CTA, [1] rounds finished by every CTA */, const bool leader) {
     constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
     const int W = q.W, H = q.H, D = q.D;
     const int len = dy == 0 ? W : H;
@@ -385,32 +392,118 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     };
     int s0 = 0;
     for (; s0 + NS + PF <= len; s0 += NS) {
+        // keep the row-sweeping warps of this CTA in step (one named barrier per 9 rows): directions that sweep the rows in the
+        // same order then touch the C and S lines they share within microseconds of each other, i.e. while they are in L2
+        if (bar_threads) {
+            asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+            if (s_pace) {
+                // global pacing (asynchronous): the helper warp publishes this CTA's progress and mirrors the grid-wide minimum into
+                // shared memory; a CTA that is more than pace_window rounds ahead of the slowest one naps.  Bounded spin: never hangs.
+                const int round = s0 / NS;
+                if (leader && lane == 0) s_pace[0] = round;
+                for (int spin = 0; spin < 4096 && round > s_pace[1] + q.pace_window; spin++) __nanosleep(128);
+            }
+        }
 #pragma unroll
         for (int u = 0; u < NS; u++) step(ring + u * STAGE, ring + ((u + PF) % NS) * STAGE, true);
     }
+    if (s_pace && leader && lane == 0) s_pace[0] = s0 / NS;  // all paced rounds done (lets the helper warp finish)
     for (int s = s0; s < len; s++) step(ring + (s % NS) * STAGE, ring + ((s + PF) % NS) * STAGE, s + PF < len);
 }
 
 template <int NR, int PF, bool FULL, bool STORE>
-__global__ void __launch_bounds__(SGM_WARPS * 32)
+__global__ void __launch_bounds__(1024)
 k_sgm_acc(SgmParams q) {
     constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int dir = blockIdx.x % q.ndirs;
-    const int line = (blockIdx.x / q.ndirs) * SGM_WARPS + warp;
+    __shared__ volatile int s_pace[2];
+    if (q.pace_arrive) {
+        if (threadIdx.x == 0) { s_pace[0] = 0; s_pace[1] = 0; }
+        __syncthreads();
+        if (warp == q.march_warps) {
+            // helper warp: all global pacing traffic happens here, off the marching warps' critical path.  arrive[r] counts the CTAs
+            // that finished round r; whoever arrives last advances the grid-wide minimum.
+            if (lane == 0) {
+                int published = 0;
+                for (int it = 0; it < (1 << 22) && published < q.pace_rounds; it++) {
+                    const int r = s_pace[0];
+                    for (; published < r; published++) {
+                        unsigned int old = atomicAdd(q.pace_arrive + published, 1u);
+                        if (old == gridDim.x - 1) { asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(q.pace_min), "r"(published + 1) : "memory"); }
+                    }
+                    unsigned int g;
+                    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(g) : "l"(q.pace_min) : "memory");
+                    s_pace[1] = (int)g;
+                    __nanosleep(1000);
+                }
+            }
+            return;
+        }
+    }
+    int dir, line;
+    if (q.balanced) {  // every CTA carries the same mix of directions and every SM the same number of CTAs -> all lines advance at the same rate
+        dir = warp % q.ndirs;
+        line = blockIdx.x + gridDim.x * (warp / q.ndirs);
+    } else {
+        dir = blockIdx.x % q.ndirs; line = (blockIdx.x / q.ndirs) * q.march_warps + warp;
+    }
     const int dx = q.dxs[dir], dy = q.dys[dir];
     if (line >= (dy == 0 ? q.H : q.W)) return;
     const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (4 * NR);
-    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE>(q, dx, dy, line, lane, ring);
-    else sgm_acc_march<NR, PF, FULL, false, STORE>(q, dx, dy, line, lane, ring);
+    int bar_threads = 0;
+    bool leader = false;
+    if (q.balanced && q.cta_sync && dy != 0) {  // threads of this CTA that march down/up the rows (all do the same number of rounds)
+        int first = -1;
+        for (int w = 0; w < q.march_warps; w++)
+            if (q.dys[w % q.ndirs] != 0 && (int)(blockIdx.x + gridDim.x * (w / q.ndirs)) < q.W) { bar_threads += 32; if (first < 0) first = w; }
+        leader = warp == first;
+    }
+    volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
+    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
+    else sgm_acc_march<NR, PF, FULL, false, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
 }
 
 template <int NR, int PF, bool FULL, bool STORE>
-static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_smem, const char* name) {
-    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
+static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_smem_per_warp, const char* name) {
+    int warps = SGM_WARPS, grid = div_up(nlines, SGM_WARPS) * q.ndirs;
+    SgmParams qq = q;
+    qq.balanced = 0;
+    qq.cta_sync = ctx->tune_sgm_cta_sync;
+    if (ctx->tune_sgm_balanced) {
+        // one wave of identical CTAs: m CTAs per SM, as few warps per CTA as cover all lines
+        for (int m = 1; m <= 8; m++) {
+            const int g = ctx->sm_count * m;
+            const int w = div_up(nlines, g) * q.ndirs;  // lines per direction per CTA x directions
+            if (w <= 32 && (size_t)w * ring_smem_per_warp * m <= 200 * 1024 && w * 32 * m <= 2048) { warps = w; grid = g; qq.balanced = 1; break; }
+        }
+    }
+    const size_t smem = (size_t)warps * ring_smem_per_warp;
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    qq.march_warps = warps;
+    qq.pace_arrive = nullptr;
+    int threads = warps * 32;
+    bool n_vert = false;
+    for (int i = 0; i < q.ndirs; i++) n_vert = n_vert || q.dys[i] != 0;
+    if (qq.balanced && qq.cta_sync && ctx->tune_sgm_pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
+        // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
+        int per_sm = 0;
+        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE>, threads + 32, smem));
+        if ((long long)per_sm * ctx->sm_count >= grid) {
+            const int rounds = (q.H - PF) / (PF + 1);
+            if (rounds > ctx->tune_sgm_pace_window) {
+                SVA_TRY(ctx->reserve(ctx->pace_buf, ((size_t)rounds + 16) * sizeof(unsigned int)));
+                SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->pace_buf.p, 0, ((size_t)rounds + 16) * sizeof(unsigned int), ctx->stream));
+                qq.pace_min = ctx->pace_buf.as<unsigned int>();
+                qq.pace_arrive = qq.pace_min + 16;
+                qq.pace_rounds = rounds;
+                qq.pace_window = ctx->tune_sgm_pace_window;
+                threads += 32;  // the helper warp
+            }
+        }
+    }
     LaunchScope ls(ctx, name);
-    k_sgm_acc<NR, PF, FULL, STORE><<<div_up(nlines, SGM_WARPS) * q.ndirs, SGM_WARPS * 32, ring_smem, ctx->stream>>>(q);
+    k_sgm_acc<NR, PF, FULL, STORE><<<grid, threads, smem, ctx->stream>>>(qq);
     return SVA_OK;
 }
 
@@ -429,10 +522,10 @@ static int launch_pass(sva_ctx* ctx, const SgmParams& q, int mode) {
         const bool full = q.lanes == 32;
         if (mode == SGM_MODE_STORE) {
             const char* nm = q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d");
-            SVA_TRY((full ? launch_acc<NR, PF, true, true>(ctx, q, nlines, ring_smem, nm) : launch_acc<NR, PF, false, true>(ctx, q, nlines, ring_smem, nm)));
+            SVA_TRY((full ? launch_acc<NR, PF, true, true>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, true>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
         } else {
             const char* nm = q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d"));
-            SVA_TRY((full ? launch_acc<NR, PF, true, false>(ctx, q, nlines, ring_smem, nm) : launch_acc<NR, PF, false, false>(ctx, q, nlines, ring_smem, nm)));
+            SVA_TRY((full ? launch_acc<NR, PF, true, false>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, false>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
         }
     } else if (mode == SGM_MODE_STORE) {
         SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_STORE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
@@ -534,6 +627,22 @@ int sva_run_sgm(sva_ctx* ctx) {
             return SVA_OK;
         }
         SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.p, 0, cells * sizeof(uint16_t), ctx->stream));
+        if (ctx->tune_sgm_split && ctx->tune_sgm_lean && n == 8) {
+            // variant C: two launches, each = the three directions sweeping the rows one way + one horizontal direction.  With a
+            // balanced grid (same CTAs on every SM) the same-sweep directions advance in step without any explicit pacing, so the
+            // C and S lines they share are still in L2 when the next direction touches them.
+            static const int down8[4] = {0, 4, 5, 2}, up8[4] = {1, 6, 7, 3};
+            for (int half = 0; half < 2; half++) {
+                static const int exp_same[4] = {0, 0, 0, 2};  // SVA_SGM_EXPERIMENT=1: L2-sharing upper bound (results are wrong)
+                const int* dd = getenv("SVA_SGM_EXPERIMENT") ? exp_same : (half ? up8 : down8);
+                q.ndirs = 4;
+                for (int i = 0; i < 4; i++) { q.dxs[i] = DIRS[dd[i]][0]; q.dys[i] = DIRS[dd[i]][1]; }
+                SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+            }
+            SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
+            ctx->have_sgm = true; ctx->have_disp = true;
+            return SVA_OK;
+        }
         q.ndirs = n;
         // interleave so that neighbouring CTAs sweep the same rows: down, down-diagonals, up, up-diagonals, horizontals
         static const int conc8[8] = {0, 4, 5, 1, 6, 7, 2, 3}, conc4[4] = {0, 1, 2, 3};

@@ -58,11 +58,18 @@ struct sva_ctx {
     int tune_sgm_pf = 8;          // SVA_SGM_PF: cp.async prefetch depth of the SGM passes (8 or 16)
     int tune_sgm_concurrent = 1;  // SVA_SGM_CONCURRENT: run the RED-accumulating SGM directions in one launch
     int tune_sgm_fused_final = 0; // SVA_SGM_FUSED_FINAL: last path + K3 in one march (variant A) instead of all-RED + WTA march
+    int tune_sgm_split = 1;       // SVA_SGM_SPLIT: two launches (down-sweeping + up-sweeping directions) instead of one
+    int tune_sgm_pace = 0;        // SVA_SGM_PACE (experimental, off): keep all CTAs of a launch within pace_window rounds of each other.
+                                  // Measured on B200 at c1: DRAM traffic per launch 2.74 -> 1.81 GB, but time 0.54 -> 0.62 ms (the grid then moves at the
+                                  // pace of its slowest CTA and becomes issue/barrier-bound), so it is not the default.
+    int tune_sgm_pace_window = 4; // SVA_SGM_PACE_WINDOW: rounds of 9 rows
+    int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
+    int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
     int tune_wta_march = 0;       // SVA_WTA_MARCH: K3 as a warp-per-row march instead of the tile kernel
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
-    DevBuf ref_img, other_imgs, lines, mask, A, C, Craw, S, disp, subpix, other_d, scratch, scratch2;
+    DevBuf ref_img, other_imgs, lines, mask, A, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
     DevBuf staging_host;  // pinned host staging for image uploads / result downloads
 
     // ---- per-kernel timing of the last run ----
