@@ -1,0 +1,46 @@
+// TEST ONLY: C-callable driver that exercises adapter/sva_functions.cpp the way the reference's main() would — through the
+// reference's own function names — on harness images (compiled against oracle/cvshim; see tests/test_gpu_adapter.py).
+#include <cstring>
+#include <string>
+
+#include "Camera.h"
+#include "functions.h"
+#include "dlibFaceSelect.h"
+
+cv::Mat svaMatchLiteral(std::vector<cv::Mat>&, std::vector<Camera>&, std::vector<std::array<int, 2>>&, cv::Mat&, int, double, double);
+
+static cv::Mat g_mask;
+cv::Mat getFaceMask(cv::Mat&) { return g_mask.clone(); }
+cv::Mat getFaceCircle(cv::Mat& m) { return getFaceMask(m); }
+static std::string g_err;
+
+extern "C" const char* adapter_last_error() { return g_err.c_str(); }
+
+// mirrors src/CameraStereoVision.cpp:23-47,98-100,112-114 with the loop nest (:49-95) replaced by ONE call
+extern "C" int adapter_driver(const uint8_t* const* images25, int w, int h, const uint8_t* mask, uint8_t* out_disp, uint8_t* out_improved, double* out_absdiff) {
+    try {
+        std::vector<cv::Mat> images;
+        for (int i = 0; i < 25; i++) {
+            cv::Mat m(h, w, CV_8UC1);
+            std::memcpy(m.data, images25[i], (size_t)w * h);
+            images.push_back(m);
+        }
+        g_mask = cv::Mat(h, w, CV_8UC1);
+        std::memcpy(g_mask.data, mask, (size_t)w * h);
+        double f = 0.05, sensor_size = 0.036, pixelSize = sensor_size / w;
+        std::vector<Camera> cameras;
+        for (int y = 0; y < 5; y++)
+            for (int x = 0; x < 5; x++) cameras.push_back(Camera(f, cv::Point3d{-0.1 + x * 0.05, -0.1 + y * 0.05, -0.75}, pixelSize));
+        std::vector<std::array<int, 2>> pairs = getCameraPairs(cameras, MID_LEFT);
+        cv::Mat m = getFaceMask(images[12]);
+        cv::Mat disparity = svaMatchLiteral(images, cameras, pairs, m, 20, 0.5, 1.0);
+        std::memcpy(out_disp, disparity.data, (size_t)w * h);
+        std::vector<cv::Mat> inpImages = {images[pairs[0][1]]};
+        std::vector<std::array<Camera, 2>> inpCameras = {{cameras[pairs[0][0]], cameras[pairs[0][1]]}};
+        cv::Mat improved = improveWithDisparity(disparity, images[pairs[0][0]], inpImages, inpCameras, 21);
+        std::memcpy(out_improved, improved.data, (size_t)w * h);
+        cv::Mat a = images[12](cv::Rect{cv::Point2i{10, 10}, cv::Point2i{50, 50}}), b = images[11](cv::Rect{cv::Point2i{12, 11}, cv::Point2i{52, 51}});
+        *out_absdiff = getAbsDiff(a, b);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}

@@ -114,7 +114,15 @@ def run_sva(args):
     cfg = configs.CONFIGS[name]
     p = configs.params(name, win_half=args.win_half)
     n_cam = p.n_pairs + 1
-    sc = configs.scene(name, frame=rank)  # every rank works on its own frame of the capture batch
+    if name == "c3":
+        return run_pair_sharded(args, rank, local_rank, world)
+    # capture batch: c4 has 64 frames per step split over the ranks (strong scaling); the others one frame per rank per step (weak)
+    from stereovisionarray_b200 import dist as sdist
+    batch = cfg["frames"]
+    fb, fe = sdist.frame_range(batch, world, rank) if batch > 1 else (rank, rank + 1)
+    frames_rank = fe - fb
+    frames_step_total = batch if batch > 1 else world
+    sc = configs.scene(name, frame=fb)  # every rank works on its own frames of the capture batch
     ctx = DepthContext(local_rank)
 
     def barrier():
@@ -137,12 +145,12 @@ def run_sva(args):
     l0 = ctx.launches()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     barrier()
-    total_ms, kern = ctx.time_detailed(abi.STAGE_ALL, args.steps)
+    total_ms, kern = ctx.time_detailed(abi.STAGE_ALL, args.steps * frames_rank)
     barrier()
     launches = ctx.launches() - l0
     total_ms = max_over_ranks(total_ms)
     mde = configs.mde_per_frame(name)
-    value = world * mde * args.steps / (total_ms / 1e3)
+    value = frames_step_total * mde * args.steps / (total_ms / 1e3)
 
     # ---- end to end: pinned host buffers -> C-ABI call -> host results ----
     def pinned(a):
@@ -157,15 +165,15 @@ def run_sva(args):
         ctx.depth_from_array(p, ref_h, others_c, mask_h, disp_h, sub_h)
     barrier()
     ctx.timer_start()
-    for _ in range(args.steps):
+    for _ in range(args.steps * frames_rank):
         ctx.depth_from_array(p, ref_h, others_c, mask_h, disp_h, sub_h)
     e2e_ms = ctx.timer_stop()
     barrier()
     clocks = sampler.stop() if sampler else None
     e2e_ms = max_over_ranks(e2e_ms)
-    e2e_value = world * mde * args.steps / (e2e_ms / 1e3)
-    h2d = n_cam * p.width * p.height + (p.width * p.height if mask_h is not None else 0)
-    d2h = p.width * p.height * (2 + 4)
+    e2e_value = frames_step_total * mde * args.steps / (e2e_ms / 1e3)
+    h2d = frames_rank * (n_cam * p.width * p.height + (p.width * p.height if mask_h is not None else 0))
+    d2h = frames_rank * p.width * p.height * (2 + 4)
 
     if rank != 0:
         if use_dist:
@@ -181,14 +189,14 @@ def run_sva(args):
         pass
     rows = []
     for kname, (sum_ms, cnt) in kern.items():
-        ab = algorithmic_bytes(kname, p, n_cam, cnt / args.steps)
+        ab = algorithmic_bytes(kname, p, n_cam, cnt / args.steps / frames_rank)
         avg_ms = sum_ms / max(1, cnt)
-        rows.append({"kernel": kname, "launches_per_step": cnt / args.steps, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
+        rows.append({"kernel": kname, "launches_per_step": cnt / args.steps / frames_rank, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
                      "algorithmic_bytes": ab, "achieved_gbs": round(ab / avg_ms / 1e6, 1) if ab else None,
                      "frac": round(ab / avg_ms / 1e6 / peak, 4) if ab else None, "traffic": traffic.get(kname)})
     rows.sort(key=lambda r: -r["share"])
     dom = next(r for r in rows if r["algorithmic_bytes"])
-    sgm_ms = sum(s for k, (s, c) in kern.items() if k.startswith("k_sgm")) / args.steps
+    sgm_ms = sum(s for k, (s, c) in kern.items() if k.startswith("k_sgm")) / args.steps / frames_rank
     sgm_bytes = (6 * p.n_paths - 4) * p.width * p.height * p.num_disp if p.n_paths else 0
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": dom["traffic"], "peak_source": peak_src, "frac_of_8000": round(dom["achieved_gbs"] / 8000.0, 4),
@@ -212,18 +220,92 @@ def run_sva(args):
                "sample": "oracle/sva_oracle.c volume pipeline (OpenMP) on a %dx%d row band of the %s frame, D=%d, %d pairs, best of 3" % (p.width, band, name, p.num_disp, p.n_pairs)}
     out = {
         "metric": "MDE/s", "value": round(value, 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u16",
-        "data": "synthetic", "frames_per_s": round(world * args.steps / (total_ms / 1e3), 2),
+        "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if batch > 1 else "weak", "vs_baseline": None, "dtype": "u16",
+        "data": "synthetic", "frames_per_s": round(frames_step_total * args.steps / (total_ms / 1e3), 2),
         "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": n_cam,
-                   "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths, "frames_per_step_per_gpu": 1,
+                   "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths, "frames_per_step_per_gpu": frames_rank,
                    "partitioning": "independent frames per GPU, no data-path collective" if world > 1 else "single GPU",
                    "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
         "e2e": {"value": round(e2e_value, 1), "unit": "MDE/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "sva_depth_from_array (C ABI, pinned host buffers)"},
         "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kernels": rows,
     }
-    print(json.dumps(out))
+    emit(json.dumps(out))
     if use_dist:
+        dist.destroy_process_group()
+
+
+def run_pair_sharded(args, rank, local_rank, world):
+    """c3: ONE frame per step; the camera pairs are split over the ranks, the packed AD partials are sum-reduced (NCCL) onto rank 0,
+    which runs the box filter, SGM and WTA.  Strong scaling.  Timed with CUDA events on torch's current stream (the library is told
+    to run on that stream so its kernels and the NCCL reduce are ordered)."""
+    import torch
+    import torch.distributed as dist
+    from stereovisionarray_b200 import dist as sdist
+    from stereovisionarray_b200.pipeline import DepthContext
+    name = "c3"
+    cfg = configs.CONFIGS[name]
+    p = configs.params(name, win_half=args.win_half)
+    sc = configs.scene(name, frame=0)
+    torch.cuda.set_device(local_rank)
+    ctx = DepthContext(local_rank)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
+    ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+    ptr, nbytes = ctx.ad_device_ptr()
+    vol = torch.as_tensor(sdist._CudaAlias(ptr, nbytes // 4), device="cuda")
+
+    def step():
+        if e > b:
+            ctx.set_pair_range(b, e)
+            ctx.run(abi.STAGE_AD)
+        else:
+            vol.zero_()
+        if world > 1:
+            dist.reduce(vol, dst=0, op=dist.ReduceOp.SUM)
+        if rank == 0:
+            ctx.mark_ad_ready()
+            ctx.run(abi.STAGE_BOX)
+            ctx.run(abi.STAGE_SGM)
+
+    for _ in range(args.warmup):
+        step()
+    torch.cuda.synchronize()
+    l0 = ctx.launches()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    clocks = sampler.stop() if sampler else None
+    launches = ctx.launches() - l0
+    if rank == 0:
+        mde = configs.mde_per_frame(name)
+        peak, peak_src = measured_peak()
+        out = {"metric": "MDE/s", "value": round(mde * args.steps / (ms / 1e3), 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
+               "frames_per_s": round(args.steps / (ms / 1e3), 3),
+               "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": p.n_pairs + 1,
+                          "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths,
+                          "partitioning": "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9),
+                          "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (nbytes / 1e6)},
+               "e2e": None, "gpu_launches": int(launches), "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "note": "see the c1 line for per-kernel rooflines"},
+               "cpu_baseline": None, "clocks": clocks}
+        emit(json.dumps(out))
+    if world > 1:
         dist.destroy_process_group()
 
 
@@ -272,7 +354,7 @@ def run_reference(args):
     name = args.config
     cfg = configs.CONFIGS[name]
     if not Reference.available():
-        print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsva_ref.so missing (built only where /root/reference exists)"}))
+        emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsva_ref.so missing (built only where /root/reference exists)"}))
         return
     import multiprocessing as mp
     cores = os.cpu_count() or 1
@@ -294,7 +376,33 @@ def run_reference(args):
            "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": w, "band_rows": band},
            "cpu_baseline": {"value": round(v, 3), "unit": "MDE/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": round(v, 3), "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
-    print(json.dumps(out))
+    emit(json.dumps(out))
+
+
+class StdoutToStderr:
+    """NCCL / torchrun print banners on fd 1; the contract is ONE JSON line on stdout, so everything else goes to stderr"""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+        return self
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        os.close(self.saved)
+
+
+_real_print = print
+
+
+def emit(line):
+    """the single JSON line, written to the REAL stdout even while fd 1 is redirected"""
+    os.write(_STDOUT_FD, (line + "\n").encode())
+
+
+_STDOUT_FD = os.dup(1)
 
 
 def main():
@@ -310,10 +418,11 @@ def main():
     ap.add_argument("--no-cpu", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "sva" else args.warmup
-    if args.impl == "reference":
-        run_reference(args)
-    else:
-        run_sva(args)
+    with StdoutToStderr():
+        if args.impl == "reference":
+            run_reference(args)
+        else:
+            run_sva(args)
 
 
 if __name__ == "__main__":

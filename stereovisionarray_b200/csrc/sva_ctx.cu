@@ -92,9 +92,17 @@ int sva_destroy(sva_ctx* c) {
 
 const char* sva_last_error(const sva_ctx* c) { return c ? c->err.c_str() : "null context"; }
 
-int sva_set_stream(sva_ctx* c, void* s) {
+int sva_set_stream(sva_ctx* c, void* s) {  // NULL = the legacy default stream (what torch.cuda.current_stream() usually is)
     if (!c) return SVA_ERR_BAD_ARG;
-    c->stream = s ? (cudaStream_t)s : c->own_stream;
+    cudaStreamSynchronize(c->stream);
+    c->stream = (cudaStream_t)s;
+    return SVA_OK;
+}
+
+int sva_use_own_stream(sva_ctx* c) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    cudaStreamSynchronize(c->stream);
+    c->stream = c->own_stream;
     return SVA_OK;
 }
 

@@ -86,7 +86,11 @@ class DepthContext:
         check(self._h, self._L.sva_synchronize(self._h))
 
     def set_stream(self, stream_ptr):
+        """run on a caller-owned CUDA stream (torch.cuda.current_stream().cuda_stream; 0 = the legacy default stream)"""
         check(self._h, self._L.sva_set_stream(self._h, C.c_void_p(stream_ptr)))
+
+    def use_own_stream(self):
+        check(self._h, self._L.sva_use_own_stream(self._h))
 
     def launches(self):
         n = C.c_uint64()

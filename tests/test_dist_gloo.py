@@ -1,0 +1,91 @@
+"""N > 1 host logic on CPU: world_size-2 (and 3) gloo process groups.  The compute backend here is the ORACLE (tests may use it);
+what is under test is the sharding + packed-int32 reduce of stereovisionarray_b200/dist.py."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from stereovisionarray_b200 import abi, dist as sdist, synth
+
+OFF15 = [(gx, gy) for gy in range(-1, 3) for gx in range(-1, 3) if (gx, gy) != (0, 0)]
+
+
+def test_partitions():
+    for n, w in [(64, 1), (64, 2), (64, 4), (64, 8), (10, 4), (3, 8), (15, 8)]:
+        rs = [sdist.frame_range(n, w, r) for r in range(w)]
+        assert rs[0][0] == 0 and rs[-1][1] == n and all(rs[i][1] == rs[i + 1][0] for i in range(w - 1))
+        assert max(e - b for b, e in rs) - min(e - b for b, e in rs) <= 1
+    assert [e - b for b, e in sdist.pair_ranges(15, 8)] == [2, 2, 2, 2, 2, 2, 2, 1]
+    assert sdist.pair_ranges(3, 8)[3:] == [(3, 3)] * 5
+    assert sdist.packed_no_carry(15) and sdist.packed_no_carry(32) and not sdist.packed_no_carry(129)
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.oracle import Oracle
+        orc = Oracle()
+        h, w, D = 40, 56, 16
+        sc = synth.make_scene(h, w, D, OFF15, 77)  # same seed on every rank: the frame is replicated
+        p = abi.make_params(w, h, D, OFF15, win_half=3, n_paths=4, lr_gx=-1)
+        b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
+        part = orc.ad_volume(p, sc["ref"], sc["others"], b, e) if e > b else np.zeros((h, w, D), np.uint16)
+        t = torch.from_numpy(sdist.numpy_pack(part).copy())
+        sdist.reduce_packed_u16(t, 0)
+        # frames: every rank processes its own frames, nothing is exchanged; gather only the checksums for the test
+        fb, fe = sdist.frame_range(5, world, rank)
+        sums = []
+        for f in range(fb, fe):
+            scf = synth.make_scene(32, 40, 16, [(-1, 0)], 4000 + f)
+            pf = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2, n_paths=4, lr_gx=-1)
+            d, _ = orc.depth_from_array(pf, scf["ref"], scf["others"])
+            sums.append((f, int(d.astype(np.int64).sum())))
+        gathered = [None] * world
+        dist.all_gather_object(gathered, sums)
+        if rank == 0:
+            full = orc.ad_volume(p, sc["ref"], sc["others"])
+            A = t.numpy().view(np.uint16).reshape(h, w, D)
+            ok_reduce = bool(np.array_equal(A, full))
+            disp, sub = orc.wta(p, orc.sgm_aggregate(p, orc.box_cost(p, A)))
+            disp1, sub1 = orc.depth_from_array(p, sc["ref"], sc["others"])
+            ok_pipe = bool(np.array_equal(disp, disp1) and np.array_equal(sub, sub1))
+            flat = sorted(x for g in gathered for x in g)
+            exp = []
+            for f in range(5):
+                scf = synth.make_scene(32, 40, 16, [(-1, 0)], 4000 + f)
+                pf = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2, n_paths=4, lr_gx=-1)
+                exp.append((f, int(orc.depth_from_array(pf, scf["ref"], scf["others"])[0].astype(np.int64).sum())))
+            q.put((ok_reduce, ok_pipe, flat == exp))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_pair_sharded_reduce_and_frame_partition(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    ok_reduce, ok_pipe, ok_frames = q.get(timeout=10)
+    assert ok_reduce, "packed int32 reduce of the AD partials != full AD volume"
+    assert ok_pipe, "pipeline from the reduced volume != single-process pipeline"
+    assert ok_frames, "frame-partitioned results != serial results"
