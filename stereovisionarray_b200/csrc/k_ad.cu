@@ -59,6 +59,8 @@ __device__ __forceinline__ void ad_gather8(const uint8_t* __restrict__ L, int of
 // one thread = CH chunks of 8 disparities of one pixel (CH = 4 when D % 32 == 0: the per-pair setup is amortised over 32 cells).
 // The chunks of a thread are interleaved with those of the other threads of the pixel (chunk = gi + groups*c), so every
 // 16-byte store instruction of a warp writes whole contiguous runs (full 32-byte sectors)
+#define TW 2
+#define TH 4
 template <int CH>
 __global__ void __launch_bounds__(256)
 k_ad_volume(const uint8_t* __restrict__ ref, size_t ref_pitch, const uint8_t* __restrict__ lines, AdPairs P, int W, int H, int D,
@@ -68,8 +70,26 @@ k_ad_volume(const uint8_t* __restrict__ ref, size_t ref_pitch, const uint8_t* __
     long long total = (long long)W * H * groups;
     if (tid >= total) return;
     int gi = (int)(tid % groups);
-    long long pix = tid / groups;
-    int x = (int)(pix % W), y = (int)(pix / W);
+    long long pt = tid / groups;
+    // pixels are visited in TW x TH micro-tiles (a warp's 8 pixels = 2 x 4): whatever the direction of a pair, the walks of a warp
+    // then fall into ~4 line-image rows instead of 8, halving the L1 wavefronts per gather
+    int x, y;
+    {
+        const int tiles_x = W / TW;
+        const long long tile = pt / (TW * TH);
+        const int in = (int)(pt % (TW * TH));
+        const long long full = (long long)tiles_x * (H / TH);
+        if (tile < full) {
+            x = (int)(tile % tiles_x) * TW + in % TW;
+            y = (int)(tile / tiles_x) * TH + in / TW;
+        } else {  // ragged right / bottom edges: plain raster over the leftover pixels
+            long long r = pt - full * (TW * TH);
+            const int wrem = W - tiles_x * TW, hfull = (H / TH) * TH;
+            if (r < (long long)wrem * hfull) { x = tiles_x * TW + (int)(r % wrem); y = (int)(r / wrem); }
+            else { r -= (long long)wrem * hfull; x = (int)(r % W); y = hfull + (int)(r / W); }
+        }
+    }
+    const long long pix = (long long)y * W + x;
     uint32_t r4 = (uint32_t)ref[(size_t)y * ref_pitch + x] * 0x01010101u;
     int delta0 = dmin + 8 * gi;
     uint32_t e0[CH], o0[CH], e1[CH], o1[CH];  // per chunk: (cells 0,2) (1,3) (4,6) (5,7) as u16x2

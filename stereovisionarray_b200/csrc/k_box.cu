@@ -33,7 +33,7 @@ __device__ __forceinline__ int axis_limit(int pos, int dim, int k, int gp, int g
     return lim;
 }
 
-#define BOX_STAGES 4
+#define BOX_STAGES 3
 
 // 16-byte async copy global -> shared; src_bytes == 0 zero-fills (out-of-image rows / columns / disparities)
 __device__ __forceinline__ void box_cp16(uint32_t dst, const void* src, int src_bytes) {
@@ -41,7 +41,7 @@ __device__ __forceinline__ void box_cp16(uint32_t dst, const void* src, int src_
 }
 
 template <int NC, bool RAW>
-__global__ void __launch_bounds__(BOX_THREADS)
+__global__ void __launch_bounds__(BOX_THREADS, NC == 8 ? 3 : 4)
 k_box_cost(BoxParams q) {
     constexpr int TXI = BOX_CG * NC;
     constexpr int ROW_BYTES = TXI * 64;                 // one tile row: TXI columns x 32 disparities x u16
