@@ -77,9 +77,9 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
     """per launch, DESIGN.md §4: s_C = s_S = 2 bytes"""
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
-    if name == "k_ad_volume":
+    if name in ("k_ad_volume", "k_ad_planar"):
         return n_cam * px + 2 * de
-    if name == "k_box_cost":
+    if name in ("k_box_cost", "k_box_planar"):
         return 4 * de
     if name.startswith("k_sgm_store"):
         return 4 * de

@@ -26,7 +26,7 @@ def _stale(out, deps):
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "sva_common.cuh"), os.path.join(HERE, "..", "include", "sva_c_api.h")]
+    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "sva_common.cuh"), os.path.join(CSRC, "sva_vec.cuh"), os.path.join(HERE, "..", "include", "sva_c_api.h")]
     if not _stale(obj, deps):
         return obj, ""
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]

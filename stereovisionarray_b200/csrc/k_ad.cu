@@ -1,6 +1,6 @@
 // k_ad.cu — K1a: per-pixel absolute-difference volume summed over camera pairs.
 //
-//   A(y,x,d) = sum_k |R(y,x) - I_k(y - gy_k*delta, x - gx_k*delta)|,  delta = min_disp + d      (u16, [H][W][D], d fastest)
+//   A(y,x,d) = sum_k |R(y,x) - I_k(y - gy_k*delta, x - gx_k*delta)|,  delta = min_disp + d      (u16; stored planar, see ApGeom)
 //
 // This is getAbsDiff's |a-b| term (reference src/functions.cpp:215-218) hoisted out of the per-candidate window loop of
 // src/CameraStereoVision.cpp:76-83: the 2k x 2k window sum is linear, so sum_pairs(box(|.|)) == box(sum_pairs(|.|)) and the
@@ -56,67 +56,67 @@ __device__ __forceinline__ void ad_gather8(const uint8_t* __restrict__ L, int of
     }
 }
 
-// one thread = CH chunks of 8 disparities of one pixel (CH = 4 when D % 32 == 0: the per-pair setup is amortised over 32 cells).
-// The chunks of a thread are interleaved with those of the other threads of the pixel (chunk = gi + groups*c), so every
-// 16-byte store instruction of a warp writes whole contiguous runs (full 32-byte sectors)
-#define TW 2
-#define TH 4
-template <int CH>
+// One thread = 8 consecutive disparities (one 16-byte chunk of the d axis) of FOUR consecutive pixels of a row.  The lanes of a
+// warp are the D/8 chunks of the same two pixel quads, so every 32-bit gather instruction of a warp reads two contiguous
+// ~(D+8)-byte runs of a line image (2-4 L1 lines instead of one per lane), and the per-pair set-up is amortised over 32 cells.
+// A CTA's work items form 8x8-pixel tiles so the sources of all pair directions stay L1-resident across the tile.
+// Output is the planar layout ApGeom (sva_common.cuh): per disparity pair one 16-byte store of 4 consecutive columns.
 __global__ void __launch_bounds__(256)
-k_ad_volume(const uint8_t* __restrict__ ref, size_t ref_pitch, const uint8_t* __restrict__ lines, AdPairs P, int W, int H, int D,
-            int dmin, uint16_t* __restrict__ A) {
-    const int groups = D / (8 * CH);
-    long long tid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-    long long total = (long long)W * H * groups;
-    if (tid >= total) return;
-    int gi = (int)(tid % groups);
-    long long pt = tid / groups;
-    // pixels are visited in TW x TH micro-tiles (a warp's 8 pixels = 2 x 4): whatever the direction of a pair, the walks of a warp
-    // then fall into ~4 line-image rows instead of 8, halving the L1 wavefronts per gather
-    int x, y;
-    {
-        const int tiles_x = W / TW;
-        const long long tile = pt / (TW * TH);
-        const int in = (int)(pt % (TW * TH));
-        const long long full = (long long)tiles_x * (H / TH);
-        if (tile < full) {
-            x = (int)(tile % tiles_x) * TW + in % TW;
-            y = (int)(tile / tiles_x) * TH + in / TW;
-        } else {  // ragged right / bottom edges: plain raster over the leftover pixels
-            long long r = pt - full * (TW * TH);
-            const int wrem = W - tiles_x * TW, hfull = (H / TH) * TH;
-            if (r < (long long)wrem * hfull) { x = tiles_x * TW + (int)(r % wrem); y = (int)(r / wrem); }
-            else { r -= (long long)wrem * hfull; x = (int)(r % W); y = hfull + (int)(r / W); }
-        }
-    }
-    const long long pix = (long long)y * W + x;
-    uint32_t r4 = (uint32_t)ref[(size_t)y * ref_pitch + x] * 0x01010101u;
-    int delta0 = dmin + 8 * gi;
-    uint32_t e0[CH], o0[CH], e1[CH], o1[CH];  // per chunk: (cells 0,2) (1,3) (4,6) (5,7) as u16x2
+k_ad_planar(const uint8_t* __restrict__ ref, size_t ref_pitch, const uint8_t* __restrict__ lines, AdPairs P, int W, int H, int D, int dmin,
+            uint32_t* __restrict__ AP, int wp, int padl, int padt) {
+    const int nch = D >> 3, per_group = 2 * nch;
+    const long long id = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long G = id / per_group;               // group = 8 consecutive pixels of one row
+    const int tl = (int)(id - G * per_group);
+    const int half = tl / nch, chunk = tl - half * nch;
+    const int tiles_x = (W + 7) >> 3;
+    const long long tile = G >> 3;
+    const int ty = (int)(tile / tiles_x), tx = (int)(tile - (long long)ty * tiles_x);
+    const int y = ty * 8 + (int)(G & 7);
+    if (y >= H) return;
+    const int x0 = tx * 8 + 4 * half;
+    int xc[4];
+    uint32_t r4[4];
 #pragma unroll
-    for (int c = 0; c < CH; c++) { e0[c] = 0; o0[c] = 0; e1[c] = 0; o1[c] = 0; }
+    for (int i = 0; i < 4; i++) {
+        xc[i] = min(x0 + i, W - 1);  // columns past the right edge compute on a clamped address and are zeroed below
+        r4[i] = (uint32_t)ref[(size_t)y * ref_pitch + xc[i]] * 0x01010101u;
+    }
+    const int delta0 = dmin + 8 * chunk;
+    uint32_t e0[4], o0[4], e1[4], o1[4];  // per pixel: cells (0,2) (1,3) (4,6) (5,7) as u16x2
+#pragma unroll
+    for (int i = 0; i < 4; i++) { e0[i] = 0; o0[i] = 0; e1[i] = 0; o1[i] = 0; }
     for (int k = 0; k < P.n; k++) {
         const uint8_t* L = lines + P.line_off[k];
-        const int g = P.g[k];
-        const int off = P.base[k] + x * P.alpha[k] + y * P.beta[k] + g * delta0;
+        const int g = P.g[k], alpha = P.alpha[k];
+        const int offb = P.base[k] + y * P.beta[k] + g * delta0;
 #pragma unroll
-        for (int c = 0; c < CH; c++) {
+        for (int i = 0; i < 4; i++) {
             uint32_t b0, b1;
-            ad_gather8(L, off + 8 * g * groups * c, g, b0, b1);
-            ad_accumulate(__vabsdiffu4(b0, r4), e0[c], o0[c]);
-            ad_accumulate(__vabsdiffu4(b1, r4), e1[c], o1[c]);
+            ad_gather8(L, offb + xc[i] * alpha, g, b0, b1);
+            ad_accumulate(__vabsdiffu4(b0, r4[i]), e0[i], o0[i]);
+            ad_accumulate(__vabsdiffu4(b1, r4[i]), e1[i], o1[i]);
         }
     }
-    uint4* out = reinterpret_cast<uint4*>(A + ((size_t)pix * D + 8 * gi));
+    uint32_t w[4][4];  // [pixel][d-pair of the chunk]
 #pragma unroll
-    for (int c = 0; c < CH; c++) {
-        uint4 v;
-        v.x = __byte_perm(e0[c], o0[c], 0x5410);  // cells 0,1
-        v.y = __byte_perm(e0[c], o0[c], 0x7632);  // cells 2,3
-        v.z = __byte_perm(e1[c], o1[c], 0x5410);
-        v.w = __byte_perm(e1[c], o1[c], 0x7632);
-        out[c * groups] = v;
+    for (int i = 0; i < 4; i++) {
+        const bool in = x0 + i < W;
+        w[i][0] = in ? __byte_perm(e0[i], o0[i], 0x5410) : 0u;
+        w[i][1] = in ? __byte_perm(e0[i], o0[i], 0x7632) : 0u;
+        w[i][2] = in ? __byte_perm(e1[i], o1[i], 0x5410) : 0u;
+        w[i][3] = in ? __byte_perm(e1[i], o1[i], 0x7632) : 0u;
     }
+    uint32_t* out = AP + ((size_t)(y + padt) * (D >> 1) + 4 * chunk) * wp + padl + x0;
+#pragma unroll
+    for (int j = 0; j < 4; j++) *reinterpret_cast<uint4*>(out + (size_t)j * wp) = make_uint4(w[0][j], w[1][j], w[2][j], w[3][j]);
+}
+
+// planar -> [H][W][D] u16 (test / download path and the RAW_U32 recomputation only)
+__global__ void k_ap_unpack(const uint32_t* __restrict__ AP, int W, int H, int dph, int wp, int padl, int padt, uint32_t* __restrict__ out) {
+    const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
+    if (x >= W) return;
+    for (int dp = 0; dp < dph; dp++) out[((size_t)y * W + x) * dph + dp] = AP[((size_t)(y + padt) * dph + dp) * wp + padl + x];
 }
 
 static void ext_gcd(int a, int b, int& g, int& u, int& v) {  // u*a + v*b = g >= 0
@@ -169,11 +169,48 @@ int sva_build_line_images(sva_ctx* ctx) {
     return SVA_OK;
 }
 
+// geometry of the planar AD volume for the current parameters; (re)allocates it and establishes its zero borders
+int sva_ap_prepare(sva_ctx* ctx) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp, k = p.win_half;
+    ApGeom g;
+    const int kk = (k + 3) & ~3;
+    g.padl = kk; g.padt = k;
+    g.txo = (256 - kk - k + 1) & ~3;
+    g.strips = div_up(W, g.txo);
+    g.wp = g.txo * (g.strips - 1) + 256;
+    const int need = kk + ((W + 7) & ~7);
+    if (g.wp < need) g.wp = need;
+    g.wp = (g.wp + 3) & ~3;
+    g.hp = H + 2 * k;
+    g.row_words = (size_t)(D >> 1) * g.wp;
+    g.words = (size_t)g.hp * g.row_words;
+    SVA_TRY(ctx->reserve(ctx->AP, g.words * 4));
+    ctx->ap = g;
+    uint64_t key = (uint64_t)(uintptr_t)ctx->AP.p;
+    key = key * 1000003u + (uint64_t)W; key = key * 1000003u + (uint64_t)H; key = key * 1000003u + (uint64_t)D; key = key * 1000003u + (uint64_t)k;
+    if (key != ctx->ap_zero_key) {  // k_ad_planar only ever writes the interior, so the borders are zeroed once per geometry
+        SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->AP.p, 0, g.words * 4, ctx->stream));
+        ctx->ap_zero_key = key;
+    }
+    return SVA_OK;
+}
+
+// planar AD volume -> ctx->A as [H][W][D] u16
+int sva_ap_unpack(sva_ctx* ctx) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp;
+    SVA_TRY(ctx->reserve(ctx->A, (size_t)W * H * D * sizeof(uint16_t)));
+    LaunchScope ls(ctx, "k_ap_unpack");
+    k_ap_unpack<<<dim3(div_up(W, 128), H), 128, 0, ctx->stream>>>(ctx->AP.as<uint32_t>(), W, H, D >> 1, ctx->ap.wp, ctx->ap.padl, ctx->ap.padt, ctx->A.as<uint32_t>());
+    SVA_CUDA_OK(ctx, cudaGetLastError());
+    return SVA_OK;
+}
+
 int sva_run_ad(sva_ctx* ctx) {
     const sva_params& p = ctx->prm;
     const int W = p.width, H = p.height, D = p.num_disp;
-    size_t cells = (size_t)W * H * D;
-    SVA_TRY(ctx->reserve(ctx->A, cells * sizeof(uint16_t)));
+    SVA_TRY(sva_ap_prepare(ctx));
     AdPairs P;
     P.n = ctx->pair_end - ctx->pair_begin;
     for (int i = 0; i < P.n; i++) {
@@ -181,16 +218,10 @@ int sva_run_ad(sva_ctx* ctx) {
         P.alpha[i] = G.alpha; P.beta[i] = G.beta; P.base[i] = G.base; P.g[i] = G.g; P.line_off[i] = G.offset;
     }
     {
-        LaunchScope ls(ctx, "k_ad_volume");
-        if (D % 32 == 0) {
-            long long threads = (long long)W * H * (D / 32);
-            k_ad_volume<4><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D,
-                                                                                     p.min_disp, ctx->A.as<uint16_t>());
-        } else {
-            long long threads = (long long)W * H * (D / 8);
-            k_ad_volume<1><<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D,
-                                                                                     p.min_disp, ctx->A.as<uint16_t>());
-        }
+        LaunchScope ls(ctx, "k_ad_planar");
+        const long long threads = (long long)div_up(W, 8) * div_up(H, 8) * 8 * (2 * (D >> 3));
+        k_ad_planar<<<(unsigned)((threads + 255) / 256), 256, 0, ctx->stream>>>(ctx->ref_img.as<uint8_t>(), (size_t)W, ctx->lines.as<uint8_t>(), P, W, H, D, p.min_disp,
+                                                                             ctx->AP.as<uint32_t>(), ctx->ap.wp, ctx->ap.padl, ctx->ap.padt);
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     ctx->have_ad = true;

@@ -192,15 +192,211 @@ int sva_launch_box(sva_ctx* ctx, const uint16_t* A, void* out, int W, int H, int
     return SVA_OK;
 }
 
+// ---- K1b on the planar AD volume (the volume pipeline's hot path) -------------------------------------------------------------
+// A warp owns ONE disparity pair (a u16x2 word per pixel) of a 256-column strip and marches down a band of rows; a lane owns 8
+// consecutive columns, i.e. 32 contiguous bytes of a plane row: two 16-byte streaming loads for the row entering the window and
+// two for the row leaving it, straight from global memory (zero borders in the layout: no bounds checks, no staging).
+//   vertical:   u = enter - leave + 0x80008000 keeps both u16 fields positive, so ONE subtraction updates two cells:
+//               F += u (the whole word, fields bleed on purpose) and Vh += u >> 16 (odd cell).  Sums are linear, so the even
+//               cell is recovered after the horizontal sum as dF - (dVh << 16); the per-row bias is a constant (arithmetic mod 2^32).
+//   horizontal: in-register prefix over the lane's 8 columns, warp shuffle scan of the lane totals, then the window sum is
+//               T[c + k] - T[c - k] on a per-warp table in shared memory (stored by (index mod 8) rows: conflict-free).
+// No __syncthreads in the arithmetic: the 8 warps of a CTA (8 d-pairs = 16 disparities = one 32-byte sector per pixel) only
+// meet to transpose their packed results through shared memory into 16-byte coalesced stores of C [H][W][D].
+#define BXP_WARPS 8
+#define BXP_TCOLS 48    // table row: 8 guard columns + 33 + 7 guard columns
+#define BXP_OPITCH 260  // words per staged output row (== 4 mod 32: the two halves of a pixel fall into different banks)
+#define BXP_MAX_BAND 1024
+
+struct BoxPParams {
+    const uint32_t* AP;
+    uint16_t* C;
+    int W, H, D, k, kk, dmin, shift, cap;
+    int gxp, gxn, gyp, gyn;
+    int band_rows, txo, wp;
+    long long row_words;
+};
+
+__global__ void __launch_bounds__(256, 2)
+k_box_planar(BoxPParams q) {
+    __shared__ __align__(16) uint32_t s_out[2][BXP_WARPS][BXP_OPITCH];
+    __shared__ uint2 s_T[BXP_WARPS][8 * BXP_TCOLS];
+    __shared__ int s_limy[BXP_MAX_BAND];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int W = q.W, H = q.H, D = q.D, k = q.k;
+    const int dpc = min((int)blockIdx.y * BXP_WARPS + warp, (D >> 1) - 1);  // warps beyond D/2 (D % 16 != 0) redo the last pair; never stored
+    const int d = 2 * dpc;
+    const int xs = blockIdx.x * q.txo - q.kk;  // image x of strip column 0
+    const int y0 = blockIdx.z * q.band_rows, y1 = min(H, y0 + q.band_rows);
+    for (int i = t; i < y1 - y0; i += 256) s_limy[i] = axis_limit(y0 + i, H, k, q.gyp, q.gyn);
+
+    int thr[8], thrmin = 0x7FFFFFFF;  // validity slack of each column for this warp's even disparity
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        thr[j] = axis_limit(xs + lane * 8 + j, W, k, q.gxp, q.gxn) - q.dmin - d;
+        thrmin = min(thrmin, thr[j]);
+    }
+    uint2* tbl = &s_T[warp][8 + lane];
+    if (lane == 0) tbl[0] = make_uint2(0u, 0u);  // T[0] = 0 (never overwritten)
+    int offh[8], offl[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        offh[j] = ((j + k) & 7) * BXP_TCOLS + ((j + k) >> 3);
+        offl[j] = ((j - k) & 7) * BXP_TCOLS + ((j - k) >> 3);  // arithmetic shift: floor
+    }
+    __syncthreads();
+
+    const uint32_t* pz = q.AP + (size_t)dpc * q.wp + (size_t)blockIdx.x * q.txo + lane * 8;  // physical row 0: zeros
+    const uint32_t* pe = pz + (size_t)y0 * q.row_words;  // update n adds physical row y0 + n (image row y0 - k + n)
+    const long long back = 2LL * k * q.row_words;
+    const int N = (y1 - y0) + 2 * k - 1;
+    uint32_t F[8], Vh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { F[j] = 0; Vh[j] = 0; }
+
+    // per-thread output items: (column, half) pairs -> one 16-byte store each, pointers advance one image row per output row
+    const int hf = t & 1;
+    const bool half_ok = (int)blockIdx.y * 16 + 8 * hf < D;
+    const int xl0 = t >> 1, xl1 = xl0 + 128;
+    const bool st0 = half_ok && xl0 >= q.kk && xl0 < q.kk + q.txo && xs + xl0 < W;
+    const bool st1 = half_ok && xl1 >= q.kk && xl1 < q.kk + q.txo && xs + xl1 < W;
+    uint16_t* po = q.C + ((size_t)y0 * W + (xs + xl0)) * D + blockIdx.y * 16 + 8 * hf;  // item 1 is 128 columns further
+    const size_t orow = (size_t)W * D;
+    const uint32_t kB = (uint32_t)k << 16;
+
+    // one update + (once the window is full) one output row; cur = this row's words, the caller keeps the next row's loads in flight
+    auto row = [&](const int n, const uint4& e0, const uint4& e1, const uint4& l0, const uint4& l1) {
+        {
+            const uint32_t ee[8] = {e0.x, e0.y, e0.z, e0.w, e1.x, e1.y, e1.z, e1.w};
+            const uint32_t ll[8] = {l0.x, l0.y, l0.z, l0.w, l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t u = ee[j] - ll[j] + 0x80008000u;
+                F[j] += u;
+                Vh[j] += u >> 16;
+            }
+        }
+        if (n < 2 * k - 1) return;
+        const int it = n - (2 * k - 1);
+        uint32_t pF[8], pV[8];
+        pF[0] = F[0]; pV[0] = Vh[0];
+#pragma unroll
+        for (int j = 1; j < 8; j++) { pF[j] = pF[j - 1] + F[j]; pV[j] = pV[j - 1] + Vh[j]; }
+        uint32_t incF = pF[7], incV = pV[7];
+#pragma unroll
+        for (int s = 1; s < 32; s <<= 1) {
+            const uint32_t a = __shfl_up_sync(0xffffffffu, incF, s), b = __shfl_up_sync(0xffffffffu, incV, s);
+            if (lane >= s) { incF += a; incV += b; }
+        }
+        const uint32_t exF = incF - pF[7], exV = incV - pV[7];
+        __syncwarp();
+#pragma unroll
+        for (int j = 0; j < 8; j++)  // T[c + 1] = inclusive prefix up to column c = lane*8 + j
+            tbl[((j + 1) & 7) * BXP_TCOLS + ((j + 1) >> 3)] = make_uint2(pF[j] + exF, pV[j] + exV);
+        __syncwarp();
+        // bias of a 2k-column window after n + 1 updates: B on the odd cell, B * 65537 on the whole-word sum
+        const uint32_t B = (uint32_t)(n + 1) * kB, B2 = B * 65537u;
+        const int srow = s_limy[it] - q.dmin - d;
+        uint32_t w[8];
+        if (__all_sync(0xffffffffu, min(thrmin, srow) >= 1)) {  // every cell of the warp's 256 x 2 cells is valid (the image interior)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint2 hi = tbl[offh[j]], lo = tbl[offl[j]];
+                const uint32_t chi = hi.y - lo.y - B;
+                const uint32_t clo = hi.x - lo.x - B2 - (chi << 16);
+                const uint32_t c0 = min(clo >> q.shift, (uint32_t)q.cap), c1 = min(chi >> q.shift, (uint32_t)q.cap);
+                w[j] = c1 * 65536u + c0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint2 hi = tbl[offh[j]], lo = tbl[offl[j]];
+                const uint32_t chi = hi.y - lo.y - B;
+                const uint32_t clo = hi.x - lo.x - B2 - (chi << 16);
+                uint32_t c0 = min(clo >> q.shift, (uint32_t)q.cap), c1 = min(chi >> q.shift, (uint32_t)q.cap);
+                const int m = min(thr[j], srow);
+                c0 = m >= 0 ? c0 : (uint32_t)q.cap;
+                c1 = m >= 1 ? c1 : (uint32_t)q.cap;
+                w[j] = c1 * 65536u + c0;
+            }
+        }
+        uint32_t* so = &s_out[it & 1][warp][lane * 8];
+        *reinterpret_cast<uint4*>(so) = make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(so + 4) = make_uint4(w[4], w[5], w[6], w[7]);
+        __syncthreads();  // one barrier per row: s_out is double-buffered
+        const uint32_t* src = &s_out[it & 1][4 * hf][xl0];
+        if (st0) *reinterpret_cast<uint4*>(po) = make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]);
+        if (st1) *reinterpret_cast<uint4*>(po + 128 * D) = make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]);
+        po += orow;
+    };
+
+    // software pipeline, unrolled by two so the row buffers ping-pong without register moves
+    uint4 a0 = ldg_stream_u128(pe), a1 = ldg_stream_u128(pe + 4), al0 = make_uint4(0, 0, 0, 0), al1 = al0;
+    uint4 b0 = a0, b1 = a1, bl0 = al0, bl1 = al1;
+    auto fetch = [&](const int n, uint4& e0, uint4& e1, uint4& l0, uint4& l1) {  // loads of update n
+        if (n < N) {
+            pe += q.row_words;
+            const uint32_t* pl = n >= 2 * k ? pe - back : pz;
+            e0 = ldg_stream_u128(pe); e1 = ldg_stream_u128(pe + 4);
+            l0 = ldg_stream_u128(pl); l1 = ldg_stream_u128(pl + 4);
+        }
+    };
+    for (int n = 0; n < N; n += 2) {
+        fetch(n + 1, b0, b1, bl0, bl1);
+        row(n, a0, a1, al0, al1);
+        if (n + 1 >= N) break;
+        fetch(n + 2, a0, a1, al0, al1);
+        row(n + 1, b0, b1, bl0, bl1);
+    }
+}
+
+int sva_ap_prepare(sva_ctx* ctx);
+int sva_ap_unpack(sva_ctx* ctx);
+
+static int sva_launch_box_planar(sva_ctx* ctx) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp, k = p.win_half;
+    BoxPParams q{};
+    q.AP = ctx->AP.as<uint32_t>(); q.C = ctx->C.as<uint16_t>();
+    q.W = W; q.H = H; q.D = D; q.k = k; q.kk = ctx->ap.padl; q.dmin = p.min_disp; q.shift = p.cost_shift; q.cap = p.cost_cap;
+    for (int i = 0; i < p.n_pairs; i++) {
+        int gx = p.pair_gx[i], gy = p.pair_gy[i];
+        if (gx > 0) q.gxp = gx > q.gxp ? gx : q.gxp;
+        if (gx < 0) q.gxn = -gx > q.gxn ? -gx : q.gxn;
+        if (gy > 0) q.gyp = gy > q.gyp ? gy : q.gyp;
+        if (gy < 0) q.gyn = -gy > q.gyn ? -gy : q.gyn;
+    }
+    q.txo = ctx->ap.txo; q.wp = ctx->ap.wp; q.row_words = (long long)ctx->ap.row_words;
+    const int strips = ctx->ap.strips, dgroups = div_up(D, 16);
+    // Row bands: every band re-reads 2k-1 warm-up rows, and the grid should fill whole waves of 2 CTAs per SM.  Pick the band
+    // count that minimises waves x rows marched per CTA.
+    const int slots = 2 * ctx->sm_count, per_band = strips * dgroups;
+    int bands = 1;
+    double best = 1e30;
+    for (int b = 1; b <= H && b <= 4096; b++) {
+        const int rows = div_up(H, b);
+        if (rows > BXP_MAX_BAND) continue;
+        if (b > 1 && rows < k) break;
+        const int nb = div_up(H, rows);
+        const double cost = (double)div_up(nb * per_band, slots) * (rows + 2 * k - 1 + 8);
+        if (cost < best) { best = cost; bands = nb; q.band_rows = rows; }
+    }
+    LaunchScope ls(ctx, "k_box_planar");
+    k_box_planar<<<dim3(strips, dgroups, bands), 256, 0, ctx->stream>>>(q);
+    SVA_CUDA_OK(ctx, cudaGetLastError());
+    return SVA_OK;
+}
+
 int sva_run_box(sva_ctx* ctx, bool raw) {
     const sva_params& p = ctx->prm;
     size_t cells = (size_t)p.width * p.height * p.num_disp;
-    if (raw) {
+    if (raw) {  // RAW_U32 recomputation (download / test path): un-planarise A, then the general kernel
         SVA_TRY(ctx->reserve(ctx->Craw, cells * sizeof(uint32_t)));
+        SVA_TRY(sva_ap_unpack(ctx));
         return sva_launch_box(ctx, ctx->A.as<uint16_t>(), ctx->Craw.p, p.width, p.height, p.num_disp, p.win_half, &p, true, true);
     }
     SVA_TRY(ctx->reserve(ctx->C, cells * sizeof(uint16_t)));
-    SVA_TRY(sva_launch_box(ctx, ctx->A.as<uint16_t>(), ctx->C.p, p.width, p.height, p.num_disp, p.win_half, &p, false, true));
+    SVA_TRY(sva_launch_box_planar(ctx));
     ctx->have_cost = true;
     return SVA_OK;
 }

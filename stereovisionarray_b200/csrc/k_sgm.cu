@@ -23,9 +23,13 @@
 #include <cstdlib>
 
 #include "sva_common.cuh"
+#include "sva_vec.cuh"
 
 // PF = steps of prefetch in flight per warp; the ring has PF + 1 stages (the slot refilled at step s was last read at step s-1)
 #define SGM_INF2 0x7FFF7FFFu
+#ifndef SGM_GROUP_REDUX
+#define SGM_GROUP_REDUX 0  // REDUX with per-group masks compiles to a divergent slow path (CREDUX writes ONE uniform register per warp)
+#endif
 #define SGM_WARPS 8
 #define SGM_FINAL_WARPS 4
 
@@ -45,6 +49,7 @@ struct SgmParams {
     unsigned int* pace_arrive;  // k_sgm_acc: [pace_rounds] CTAs that finished round r (nullptr = no global pacing)
     unsigned int* pace_min;     // rounds finished by every CTA
     int pace_rounds, pace_window, march_warps;
+    int exp_no_out;     // timing experiment only (SVA_SGM_EXP=1): run the recurrence but drop the S updates
     int cta_sync;       // k_sgm_acc (balanced): named barrier among the row-sweeping warps of a CTA every round
     int balanced;       // k_sgm_acc: grid = m * SM count; warp w of CTA b handles direction w % ndirs, line b + grid * (w / ndirs)
     const uint8_t* mask;
@@ -52,57 +57,14 @@ struct SgmParams {
     float* sub;
 };
 
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
-
-template <int NR> struct Vec;
-template <> struct Vec<1> {
-    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[1]) { r[0] = ldg_stream_u32(p); }
-    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[1]) {
-        asm volatile("ld.global.L1::no_allocate.u32 %0, [%1];" : "=r"(r[0]) : "l"(p));
-    }
-    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(dst), "l"(p) : "memory"); }
-    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[1]) { asm volatile("ld.shared.u32 %0, [%1];" : "=r"(r[0]) : "r"(src)); }
-    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[1]) { *reinterpret_cast<uint32_t*>(p) = r[0]; }
-    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[1]) {
-        asm volatile("red.global.add.u32 [%0], %1;" ::"l"(p), "r"(r[0]) : "memory");
-    }
-};
-template <> struct Vec<2> {
-    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[2]) { uint2 v = ldg_stream_u64(p); r[0] = v.x; r[1] = v.y; }
-    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[2]) {
-        asm volatile("ld.global.L1::no_allocate.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "l"(p));
-    }
-    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p) : "memory"); }
-    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[2]) { asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(src)); }
-    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[2]) { *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]); }
-    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[2]) {
-        unsigned long long v = ((unsigned long long)r[1] << 32) | r[0];
-        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-    }
-};
-template <> struct Vec<4> {
-    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[4]) { uint4 v = ldg_stream_u128(p); r[0] = v.x; r[1] = v.y; r[2] = v.z; r[3] = v.w; }
-    static __device__ __forceinline__ void load_rw(const uint16_t* p, uint32_t (&r)[4]) {
-        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "l"(p));
-    }
-    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) { asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(p) : "memory"); }
-    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[4]) { asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(src)); }
-    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[4]) { *reinterpret_cast<uint4*>(p) = make_uint4(r[0], r[1], r[2], r[3]); }
-    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[4]) {
-        unsigned long long v0 = ((unsigned long long)r[1] << 32) | r[0], v1 = ((unsigned long long)r[3] << 32) | r[2];
-        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v0) : "memory");
-        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p + 4), "l"(v1) : "memory");
-    }
-};
-
 // one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
-template <int NR>
+// LPL = lanes per path line: 32 (one line per warp) or 16 / 8 (two / four lines per warp — more cells per lane, so the
+// shuffles, the minimum reduction and the loop overhead are amortised over more cells)
+template <int NR, int LPL = 32>
 __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)[NR], uint32_t& mm, uint32_t& mp2, uint32_t p1p1, uint32_t p2p2,
                                          bool first_lane, bool last_lane) {
-    uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+    uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1, LPL);
+    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1, LPL);
     if (first_lane) up = SGM_INF2;
     if (last_lane) dn = SGM_INF2;
     uint32_t sh[NR + 1];  // sh[j] = values at d-1 of register j; sh[j+1] = values at d+1 of register j
@@ -119,8 +81,19 @@ __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)
         L[j] = Cc[j] + t - mm;  // both halves: t >= mm, no borrow; C + t - mm <= 8190, no carry
         mloc = __vminu2(mloc, L[j]);
     }
-    uint32_t m = min(mloc & 0xFFFFu, mloc >> 16);
-    m = __reduce_min_sync(0xffffffffu, m);
+    uint32_t m;
+    if (LPL == 32) {
+        m = min(mloc & 0xFFFFu, mloc >> 16);
+        m = __reduce_min_sync(0xffffffffu, m);
+    } else if (SGM_GROUP_REDUX) {  // one REDUX per group: the groups of a warp pass disjoint member masks
+        m = min(mloc & 0xFFFFu, mloc >> 16);
+        const unsigned lane = threadIdx.x & 31u;
+        m = __reduce_min_sync(((1u << LPL) - 1u) << (lane & ~(unsigned)(LPL - 1)), m);
+    } else {
+#pragma unroll
+        for (int o = LPL / 2; o > 0; o >>= 1) mloc = __vminu2(mloc, __shfl_xor_sync(0xffffffffu, mloc, o, LPL));
+        m = min(mloc & 0xFFFFu, mloc >> 16);
+    }
     mm = m * 0x10001u;
     mp2 = mm + p2p2;
 }
@@ -339,33 +312,35 @@ k_sgm_pass(SgmParams q) {
 
 // ---- lean accumulate march (the hot kernel): same recurrence and ring as above, specialised at compile time on
 // DIAG (wrap/restart logic only for diagonals), FULL (all 32 lanes active: no predicates) and STORE (plain store vs RED),
-// running 64-bit cursors instead of recomputed cell indices, and an unchecked steady-state loop with a checked tail.
-template <int NR, int PF, bool FULL, bool DIAG, bool STORE>
-__device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t ring, const int bar_threads,
-                                              volatile int* s_pace /* [0] rounds finished by this CTA, [1] rounds finished by every CTA */, const bool leader) {
+// running 32-bit element cursors instead of recomputed cell indices, and an unchecked steady-state loop with a checked tail.
+template <int NR, int PF, bool FULL, bool DIAG, bool STORE, int LPL>
+__device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const bool do_out, const int lane, const uint32_t ring,
+                                              const int bar_threads, volatile int* s_pace /* [0] rounds finished by this CTA, [1] rounds finished by every CTA */,
+                                              const bool leader) {
     constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
     const int W = q.W, H = q.H, D = q.D;
     const int len = dy == 0 ? W : H;
     const int x0 = dy == 0 ? (dx > 0 ? 0 : W - 1) : line, y0 = dy == 0 ? line : (dy > 0 ? 0 : H - 1);
-    const long long dstep = ((long long)dy * W + dx) * D, wrapfix = -(long long)dx * W * D;
-    const long long start = ((long long)y0 * W + x0) * D + lane * NV;
-    const uint16_t* pc = q.C + start;  // prefetch cursor
-    uint16_t* ps = q.S + start;        // accumulate cursor
-    int xc = x0, xs = x0;
-    const bool active = FULL || lane < q.lanes;
-    const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
-    auto adv = [&](auto& p, int& xx) -> bool {
-        p += dstep;
+    // Cursors are 32-bit ELEMENT indices into the volumes (W*H*D < 2^32; the 64-bit address is one IMAD.WIDE on the FMA pipe), and
+    // a diagonal's wrap at the image edge is a countdown instead of two coordinate compares: the recurrence saturates the integer
+    // ALU pipe, so every ALU instruction shaved off the cursor bookkeeping is time.
+    const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
+    const int lin = lane % LPL;  // lane within this line's group (LPL lanes per line, 32 / LPL lines per warp)
+    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lin * NV);
+    uint32_t ic = start, is = start;                  // prefetch cursor (C), accumulate cursor (S)
+    int cc = dx > 0 ? W - x0 : x0 + 1, cs = cc;       // steps until each cursor leaves the image sideways
+    const bool active = FULL || lin < q.lanes;
+    const bool first_lane = lin == 0, last_lane = FULL ? lin == LPL - 1 : lin == q.lanes - 1;
+    auto adv = [&](uint32_t& i, int& cnt) -> bool {
+        i += dstep;
         if (DIAG) {
-            xx += dx;
-            if (xx >= W) { xx = 0; p += wrapfix; return true; }
-            if (xx < 0) { xx = W - 1; p += wrapfix; return true; }
+            if (--cnt == 0) { cnt = W; i += wrapfix; return true; }
         }
         return false;
     };
 #pragma unroll
     for (int u = 0; u < PF; u++) {
-        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, pc); adv(pc, xc); }
+        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc); }
         cp_async_commit();
     }
     uint32_t L[NR];
@@ -379,16 +354,16 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
 #pragma unroll
         for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
         if (active) Vec<NR>::lds(slot_addr, Cc);
-        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, pc); adv(pc, xc); }
+        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); adv(ic, cc); }
         cp_async_commit();
         if (DIAG && restart) {
 #pragma unroll
             for (int j = 0; j < NR; j++) L[j] = 0;
             mm = 0; mp2 = q.p2p2;
         }
-        sgm_step<NR>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
-        if (active) { if (STORE) Vec<NR>::store(ps, L); else Vec<NR>::red(ps, L); }
-        restart = adv(ps, xs);
+        sgm_step<NR, LPL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+        if (active && do_out) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
+        restart = adv(is, cs);
     };
     int s0 = 0;
     for (; s0 + NS + PF <= len; s0 += NS) {
@@ -411,9 +386,10 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     for (int s = s0; s < len; s++) step(ring + (s % NS) * STAGE, ring + ((s + PF) % NS) * STAGE, s + PF < len);
 }
 
-template <int NR, int PF, bool FULL, bool STORE>
+template <int NR, int PF, bool FULL, bool STORE, int LPL>
 __global__ void __launch_bounds__(1024)
 k_sgm_acc(SgmParams q) {
+    constexpr int LPW = 32 / LPL;  // path lines per warp
     constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -441,31 +417,36 @@ k_sgm_acc(SgmParams q) {
             return;
         }
     }
-    int dir, line;
+    int dir, wline;  // wline = index of this warp's group of LPW consecutive lines
     if (q.balanced) {  // every CTA carries the same mix of directions and every SM the same number of CTAs -> all lines advance at the same rate
         dir = warp % q.ndirs;
-        line = blockIdx.x + gridDim.x * (warp / q.ndirs);
+        wline = blockIdx.x + gridDim.x * (warp / q.ndirs);
     } else {
-        dir = blockIdx.x % q.ndirs; line = (blockIdx.x / q.ndirs) * q.march_warps + warp;
+        dir = blockIdx.x % q.ndirs; wline = (blockIdx.x / q.ndirs) * q.march_warps + warp;
     }
     const int dx = q.dxs[dir], dy = q.dys[dir];
-    if (line >= (dy == 0 ? q.H : q.W)) return;
+    const int nlines = dy == 0 ? q.H : q.W;
+    if (wline * LPW >= nlines) return;
+    int line = wline * LPW + lane / LPL;
+    const bool do_out = line < nlines && !q.exp_no_out;  // a ragged last group recomputes the last line and drops the result
+    line = min(line, nlines - 1);
     const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (4 * NR);
     int bar_threads = 0;
     bool leader = false;
     if (q.balanced && q.cta_sync && dy != 0) {  // threads of this CTA that march down/up the rows (all do the same number of rounds)
         int first = -1;
         for (int w = 0; w < q.march_warps; w++)
-            if (q.dys[w % q.ndirs] != 0 && (int)(blockIdx.x + gridDim.x * (w / q.ndirs)) < q.W) { bar_threads += 32; if (first < 0) first = w; }
+            if (q.dys[w % q.ndirs] != 0 && (int)(blockIdx.x + gridDim.x * (w / q.ndirs)) * LPW < q.W) { bar_threads += 32; if (first < 0) first = w; }
         leader = warp == first;
     }
     volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
-    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
-    else sgm_acc_march<NR, PF, FULL, false, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
+    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
+    else sgm_acc_march<NR, PF, FULL, false, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
 }
 
-template <int NR, int PF, bool FULL, bool STORE>
-static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_smem_per_warp, const char* name) {
+template <int NR, int PF, bool FULL, bool STORE, int LPL>
+static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines_all, size_t ring_smem_per_warp, const char* name) {
+    const int nlines = div_up(nlines_all, 32 / LPL);  // warp-lines
     int warps = SGM_WARPS, grid = div_up(nlines, SGM_WARPS) * q.ndirs;
     SgmParams qq = q;
     qq.balanced = 0;
@@ -479,7 +460,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_
         }
     }
     const size_t smem = (size_t)warps * ring_smem_per_warp;
-    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, LPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     qq.march_warps = warps;
     qq.pace_arrive = nullptr;
     int threads = warps * 32;
@@ -488,7 +469,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_
     if (qq.balanced && qq.cta_sync && ctx->tune_sgm_pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
         // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
         int per_sm = 0;
-        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE>, threads + 32, smem));
+        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, LPL>, threads + 32, smem));
         if ((long long)per_sm * ctx->sm_count >= grid) {
             const int rounds = (q.H - PF) / (PF + 1);
             if (rounds > ctx->tune_sgm_pace_window) {
@@ -503,7 +484,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines, size_t ring_
         }
     }
     LaunchScope ls(ctx, name);
-    k_sgm_acc<NR, PF, FULL, STORE><<<grid, threads, smem, ctx->stream>>>(qq);
+    k_sgm_acc<NR, PF, FULL, STORE, LPL><<<grid, threads, smem, ctx->stream>>>(qq);
     return SVA_OK;
 }
 
@@ -522,10 +503,10 @@ static int launch_pass(sva_ctx* ctx, const SgmParams& q, int mode) {
         const bool full = q.lanes == 32;
         if (mode == SGM_MODE_STORE) {
             const char* nm = q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d");
-            SVA_TRY((full ? launch_acc<NR, PF, true, true>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, true>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
+            SVA_TRY((full ? launch_acc<NR, PF, true, true, 32>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, true, 32>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
         } else {
             const char* nm = q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d"));
-            SVA_TRY((full ? launch_acc<NR, PF, true, false>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, false>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
+            SVA_TRY((full ? launch_acc<NR, PF, true, false, 32>(ctx, q, nlines, ring_smem / SGM_WARPS, nm) : launch_acc<NR, PF, false, false, 32>(ctx, q, nlines, ring_smem / SGM_WARPS, nm)));
         }
     } else if (mode == SGM_MODE_STORE) {
         SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_pass<NR, SGM_MODE_STORE, PF>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)ring_smem));
@@ -540,8 +521,58 @@ static int launch_pass(sva_ctx* ctx, const SgmParams& q, int mode) {
     return SVA_OK;
 }
 
+// several path lines per warp (LPL = 16 or 8 lanes per line, every lane active): accumulate passes only
+template <int NR, int LPL>
+static int launch_multi(sva_ctx* ctx, const SgmParams& q, int mode) {
+    constexpr int PF = 8;
+    int nlines = 0;
+    for (int i = 0; i < q.ndirs; i++) nlines = std::max(nlines, q.dys[i] == 0 ? q.H : q.W);
+    const size_t ring_per_warp = (size_t)(PF + 1) * 32 * 2 * NR * 2;
+    const char* nm = mode == SGM_MODE_STORE ? (q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d"))
+                                            : (q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d")));
+    static const int exp = getenv("SVA_SGM_EXP") ? atoi(getenv("SVA_SGM_EXP")) : 0;  // timing experiments (results are wrong): 1 = no S updates, 2 = plain stores
+    if (exp == 1) { SgmParams qq = q; qq.exp_no_out = 1; return launch_acc<NR, PF, true, false, LPL>(ctx, qq, nlines, ring_per_warp, nm); }
+    if (mode == SGM_MODE_STORE || exp == 2) SVA_TRY((launch_acc<NR, PF, true, true, LPL>(ctx, q, nlines, ring_per_warp, nm)));
+    else SVA_TRY((launch_acc<NR, PF, true, false, LPL>(ctx, q, nlines, ring_per_warp, nm)));
+    SVA_CUDA_OK(ctx, cudaGetLastError());
+    return SVA_OK;
+}
+
+// lanes per line for the accumulate passes: 16 / 8 when D splits evenly into 2, 4, 8, 12 or 16 cells per lane, else 32
+static int sgm_multi_lpl(const sva_ctx* ctx, int D) {
+    const int want = ctx->tune_sgm_lpl;
+    if (!ctx->tune_sgm_lean || (want != 16 && want != 8)) return 32;
+    for (int lpl = want; lpl <= 16; lpl *= 2) {
+        if (D % (2 * lpl)) continue;
+        const int nr = D / (2 * lpl);
+        if (nr == 1 || nr == 2 || nr == 4 || nr == 8 || (nr == 6 && lpl == 16)) return lpl;
+    }
+    return 32;
+}
+
 static int launch_pass_nr(sva_ctx* ctx, const SgmParams& q, int nr, int mode) {
     const int pf = ctx->tune_sgm_pf;
+    const int lpl = mode == SGM_MODE_FINAL ? 32 : sgm_multi_lpl(ctx, q.D);
+    if (lpl != 32) {
+        SgmParams qq = q;
+        qq.lanes = lpl;
+        const int nrm = q.D / (2 * lpl);
+        if (lpl == 16) {
+            switch (nrm) {
+                case 1: return launch_multi<1, 16>(ctx, qq, mode);
+                case 2: return launch_multi<2, 16>(ctx, qq, mode);
+                case 4: return launch_multi<4, 16>(ctx, qq, mode);
+                case 6: return launch_multi<6, 16>(ctx, qq, mode);
+                default: return launch_multi<8, 16>(ctx, qq, mode);
+            }
+        }
+        switch (nrm) {
+            case 1: return launch_multi<1, 8>(ctx, qq, mode);
+            case 2: return launch_multi<2, 8>(ctx, qq, mode);
+            case 4: return launch_multi<4, 8>(ctx, qq, mode);
+            default: return launch_multi<8, 8>(ctx, qq, mode);
+        }
+    }
     switch (nr) {
         case 1: return pf >= 16 ? launch_pass<1, 16>(ctx, q, mode) : launch_pass<1, 8>(ctx, q, mode);
         case 2: return pf >= 16 ? launch_pass<2, 16>(ctx, q, mode) : launch_pass<2, 8>(ctx, q, mode);
@@ -631,6 +662,33 @@ int sva_run_sgm(sva_ctx* ctx) {
             // variant C: two launches, each = the three directions sweeping the rows one way + one horizontal direction.  With a
             // balanced grid (same CTAs on every SM) the same-sweep directions advance in step without any explicit pacing, so the
             // C and S lines they share are still in L2 when the next direction touches them.
+            if (ctx->tune_sgm_split == 3) {  // variant E: all six row-sweeping directions in one launch (down and up sweeps cross mid-image), then the horizontals
+                static const int rows6[6] = {0, 4, 5, 1, 6, 7}, hor2[2] = {2, 3};
+                q.ndirs = 6;
+                for (int i = 0; i < 6; i++) { q.dxs[i] = DIRS[rows6[i]][0]; q.dys[i] = DIRS[rows6[i]][1]; }
+                SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+                q.ndirs = 2;
+                for (int i = 0; i < 2; i++) { q.dxs[i] = DIRS[hor2[i]][0]; q.dys[i] = DIRS[hor2[i]][1]; }
+                SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+                SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
+                ctx->have_sgm = true; ctx->have_disp = true;
+                return SVA_OK;
+            }
+            if (ctx->tune_sgm_split == 2) {
+                // variant D: three launches — the three directions sweeping the rows downwards, the three sweeping upwards, and the
+                // two horizontal ones.  A row-sweeping launch holds only lines that advance one row per step, so (paced) all of them
+                // touch a row's C and S lines while these are in L2: DRAM sees C once and S once per launch instead of once per
+                // direction.  The horizontal lines (W steps each, every row in flight at once) cannot share and get their own launch.
+                static const int grp[3][3] = {{0, 4, 5}, {1, 6, 7}, {2, 3, -1}};
+                for (int g = 0; g < 3; g++) {
+                    q.ndirs = g == 2 ? 2 : 3;
+                    for (int i = 0; i < q.ndirs; i++) { q.dxs[i] = DIRS[grp[g][i]][0]; q.dys[i] = DIRS[grp[g][i]][1]; }
+                    SVA_TRY(launch_pass_nr(ctx, q, nr, SGM_MODE_RED));
+                }
+                SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
+                ctx->have_sgm = true; ctx->have_disp = true;
+                return SVA_OK;
+            }
             static const int down8[4] = {0, 4, 5, 2}, up8[4] = {1, 6, 7, 3};
             for (int half = 0; half < 2; half++) {
                 static const int exp_same[4] = {0, 0, 0, 2};  // SVA_SGM_EXPERIMENT=1: L2-sharing upper bound (results are wrong)

@@ -8,6 +8,8 @@ int sva_run_ad(sva_ctx* ctx);
 int sva_run_box(sva_ctx* ctx, bool raw);
 int sva_run_sgm(sva_ctx* ctx);
 int sva_sgm_regs_per_lane(int D);
+int sva_ap_prepare(sva_ctx* ctx);
+int sva_ap_unpack(sva_ctx* ctx);
 
 static int check_params(sva_ctx* c, const sva_params* p) {
     if (!p) return c->fail(SVA_ERR_BAD_ARG, "null params");
@@ -194,7 +196,13 @@ static int download(sva_ctx* c, bool have, const DevBuf& b, void* out, size_t by
 
 static size_t cells(const sva_ctx* c) { return (size_t)c->prm.width * c->prm.height * c->prm.num_disp; }
 
-int sva_frame_download_ad(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_ad, c->A, out, cells(c) * 2, "AD volume"); }
+int sva_frame_download_ad(sva_ctx* c, uint16_t* out) {
+    if (!c || !out) return SVA_ERR_BAD_ARG;
+    if (!c->have_ad) return c->fail(SVA_ERR_STATE, "not computed yet: AD volume");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(sva_ap_unpack(c));  // the device volume is planar (ApGeom); the C ABI hands out [H][W][D]
+    return download(c, true, c->A, out, cells(c) * 2, "AD volume");
+}
 int sva_frame_download_cost(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_cost, c->C, out, cells(c) * 2, "cost volume"); }
 int sva_frame_download_sgm(sva_ctx* c, uint16_t* out) { return download(c, c && c->have_sgm, c->S, out, cells(c) * 2, "aggregated volume"); }
 int sva_frame_download_raw_cost(sva_ctx* c, uint32_t* out) {
@@ -219,8 +227,8 @@ int sva_frame_ad_device_ptr(sva_ctx* c, void** out_ptr, size_t* out_bytes) {
     if (!c || !out_ptr || !out_bytes) return SVA_ERR_BAD_ARG;
     if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
-    SVA_TRY(c->reserve(c->A, cells(c) * 2));
-    *out_ptr = c->A.p; *out_bytes = cells(c) * 2;
+    SVA_TRY(sva_ap_prepare(c));  // planar layout incl. its zero borders: a cross-GPU sum is element-wise, so the layout does not matter
+    *out_ptr = c->AP.p; *out_bytes = c->ap.words * 4;
     return SVA_OK;
 }
 /* after an external (cross-GPU) reduction wrote the full A volume into the buffer above */

@@ -36,6 +36,14 @@ struct PairGeom {
     size_t offset;              // byte offset of this pair's line image inside ctx->lines
 };
 
+// Planar layout of the AD volume ("AP"): u16x2 words [Hp][D/2][Wp] — one plane per disparity PAIR and row, x fastest, with
+// zero borders of padt rows above / below and padl columns left (k_ad.cu writes the interior, k_box.cu streams it).
+struct ApGeom {
+    int wp = 0, hp = 0, padl = 0, padt = 0;  // physical width / height in words / rows, left / top zero border
+    int txo = 0, strips = 0;                 // k_box_planar: output columns per 256-column strip, strips per row
+    size_t row_words = 0, words = 0;         // (D/2) * wp, hp * row_words
+};
+
 struct KernelTime {
     const char* name;
     cudaEvent_t beg, end;
@@ -58,7 +66,7 @@ struct sva_ctx {
     int tune_sgm_pf = 8;          // SVA_SGM_PF: cp.async prefetch depth of the SGM passes (8 or 16)
     int tune_sgm_concurrent = 1;  // SVA_SGM_CONCURRENT: run the RED-accumulating SGM directions in one launch
     int tune_sgm_fused_final = 0; // SVA_SGM_FUSED_FINAL: last path + K3 in one march (variant A) instead of all-RED + WTA march
-    int tune_sgm_split = 1;       // SVA_SGM_SPLIT: two launches (down-sweeping + up-sweeping directions) instead of one
+    int tune_sgm_split = 2;       // SVA_SGM_SPLIT: 0 = one launch, 1 = two (down + right, up + left), 2 = three (down-sweeping, up-sweeping, horizontal; default), 3 = six row-sweeping + two horizontal
     int tune_sgm_pace = 0;        // SVA_SGM_PACE (experimental, off): keep all CTAs of a launch within pace_window rounds of each other.
                                   // Measured on B200 at c1: DRAM traffic per launch 2.74 -> 1.81 GB, but time 0.54 -> 0.62 ms (the grid then moves at the
                                   // pace of its slowest CTA and becomes issue/barrier-bound), so it is not the default.
@@ -66,10 +74,14 @@ struct sva_ctx {
     int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
     int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
+    int tune_sgm_lpl = 32;        // SVA_SGM_LPL: lanes per path line in the accumulate passes (32 = one line per warp, 16 / 8 = two / four)
+    int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)
     int tune_wta_march = 0;       // SVA_WTA_MARCH: K3 as a warp-per-row march instead of the tile kernel
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
-    DevBuf ref_img, other_imgs, lines, mask, A, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
+    DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
+    ApGeom ap;
+    uint64_t ap_zero_key = 0;  // geometry + buffer the zero borders of AP were last established for
     DevBuf staging_host;  // pinned host staging for image uploads / result downloads
 
     // ---- per-kernel timing of the last run ----

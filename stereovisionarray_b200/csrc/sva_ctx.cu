@@ -71,6 +71,8 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_BALANCED")) c->tune_sgm_balanced = atoi(e);
     if (const char* e = getenv("SVA_SGM_CTA_SYNC")) c->tune_sgm_cta_sync = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
+    if (const char* e = getenv("SVA_SGM_LPL")) c->tune_sgm_lpl = atoi(e);
+    if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE_WINDOW")) c->tune_sgm_pace_window = atoi(e);
     *out = c;
     return SVA_OK;
@@ -80,7 +82,7 @@ int sva_destroy(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
+    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->staging_host.p) cudaFreeHost(c->staging_host.p);

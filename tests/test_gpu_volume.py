@@ -27,6 +27,8 @@ CASES = [
     (60, 88, 32, OFF15, dict(win_half=20, n_paths=8, lr_gx=0)),
     (61, 83, 16, [(0, -1), (2, 1)], dict(win_half=2, n_paths=4, lr_gx=-1, subpixel=0)),
     (50, 70, 96, [(-1, 0), (0, 1)], dict(win_half=13, n_paths=0, lr_gx=-1)),
+    (40, 611, 40, OFF8, dict(win_half=7, n_paths=4, lr_gx=-1)),   # several 256-column box strips, win_half % 4 != 0, D % 16 != 0, ragged width
+    (150, 300, 24, [(1, 0), (0, -1), (-1, 1)], dict(win_half=9, n_paths=8, lr_gx=1, min_disp=2)),  # several row bands
 ]
 
 
