@@ -77,7 +77,7 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
     """per launch, DESIGN.md §4: s_C = s_S = 2 bytes"""
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
-    if name in ("k_ad_volume", "k_ad_planar"):
+    if name in ("k_ad_volume", "k_ad_planar", "k_ad_tile"):
         return n_cam * px + 2 * de
     if name in ("k_box_cost", "k_box_planar"):
         return 4 * de
@@ -88,6 +88,10 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
         return 6 * de * dirs / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
     if name in ("k_wta_march", "k_wta_tile"):
         return 2 * de + 6 * px
+    if name == "k_wta_seg":
+        return 2 * de + 6 * px   # S once, winner map + the other view's key map
+    if name == "k_wta_finish":
+        return 18 * px           # winner, key, mask, three S cells, u16 + f32 outputs
     if name == "k_lr_check":
         return 10 * px
     if name.startswith("k_sgm_red"):

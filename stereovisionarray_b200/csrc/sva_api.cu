@@ -9,6 +9,10 @@ int sva_run_box(sva_ctx* ctx, bool raw);
 int sva_run_sgm(sva_ctx* ctx);
 int sva_sgm_regs_per_lane(int D);
 int sva_ap_prepare(sva_ctx* ctx);
+bool sva_ad2_usable(const sva_params& p);
+int sva_ad2_prepare(sva_ctx* ctx);
+uint8_t* sva_ad2_view_origin(sva_ctx* ctx, int k);
+int sva_run_ad2(sva_ctx* ctx);
 int sva_ap_unpack(sva_ctx* ctx);
 
 static int check_params(sva_ctx* c, const sva_params* p) {
@@ -49,17 +53,26 @@ int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, c
     c->pair_begin = 0; c->pair_end = p->n_pairs;
     c->have_frame = c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;
     const size_t img = (size_t)W * H;
-    SVA_TRY(c->reserve(c->ref_img, img));
-    SVA_TRY(c->reserve(c->other_imgs, img * p->n_pairs));
-    SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->ref_img.p, W, ref->data, ref->step, W, H, cudaMemcpyHostToDevice, c->stream));
-    for (int i = 0; i < p->n_pairs; i++)
-        SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->other_imgs.as<uint8_t>() + img * i, W, others[i].data, others[i].step, W, H, cudaMemcpyHostToDevice, c->stream));
+    c->use_ad2 = sva_ad2_usable(*p) && !c->tune_ad_gather;
+    if (c->use_ad2) {
+        // image-space AD kernel: the views go straight from the host into zero-bordered, 16-byte-pitched device copies
+        SVA_TRY(sva_ad2_prepare(c));
+        SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->pad_ref.p, c->ad2.rp, ref->data, ref->step, W, H, cudaMemcpyHostToDevice, c->stream));
+        for (int i = 0; i < p->n_pairs; i++)
+            SVA_CUDA_OK(c, cudaMemcpy2DAsync(sva_ad2_view_origin(c, i), c->ad2.pp, others[i].data, others[i].step, W, H, cudaMemcpyHostToDevice, c->stream));
+    } else {
+        SVA_TRY(c->reserve(c->ref_img, img));
+        SVA_TRY(c->reserve(c->other_imgs, img * p->n_pairs));
+        SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->ref_img.p, W, ref->data, ref->step, W, H, cudaMemcpyHostToDevice, c->stream));
+        for (int i = 0; i < p->n_pairs; i++)
+            SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->other_imgs.as<uint8_t>() + img * i, W, others[i].data, others[i].step, W, H, cudaMemcpyHostToDevice, c->stream));
+    }
     c->has_mask = mask != nullptr;
     if (mask) {
         SVA_TRY(c->reserve(c->mask, img));
         SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->mask.p, W, mask->data, mask->step, W, H, cudaMemcpyHostToDevice, c->stream));
     }
-    SVA_TRY(sva_build_line_images(c));
+    if (!c->use_ad2) SVA_TRY(sva_build_line_images(c));
     c->have_frame = true;
     return SVA_OK;
 }
@@ -82,7 +95,7 @@ static int run_stage(sva_ctx* c, int stage) {
     switch (stage) {
         case SVA_STAGE_AD:
             if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
-            return sva_run_ad(c);
+            return c->use_ad2 ? sva_run_ad2(c) : sva_run_ad(c);
         case SVA_STAGE_BOX:
             if (!c->have_ad) return c->fail(SVA_ERR_STATE, "AD volume not computed");
             return sva_run_box(c, false);

@@ -44,6 +44,13 @@ struct ApGeom {
     size_t row_words = 0, words = 0;         // (D/2) * wp, hp * row_words
 };
 
+// Zero-bordered, 16-byte-pitched device copies of the views for the image-space AD kernel (k_ad2.cu).
+struct Ad2Geom {
+    int padx = 0, pady = 0, pp = 0, rows = 0;  // other views: left / top border, pitch, padded height
+    int rp = 0, ref_rows = 0;                  // reference view: pitch, padded height
+    size_t img_bytes = 0;                      // bytes per padded other view
+};
+
 struct KernelTime {
     const char* name;
     cudaEvent_t beg, end;
@@ -75,11 +82,16 @@ struct sva_ctx {
     int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
     int tune_sgm_lpl = 32;        // SVA_SGM_LPL: lanes per path line in the accumulate passes (32 = one line per warp, 16 / 8 = two / four)
+    int tune_ad_gather = 0;       // SVA_AD_GATHER=1: force the line-image gather AD kernel (k_ad.cu) even where the image-space kernel applies
     int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)
     int tune_wta_march = 0;       // SVA_WTA_MARCH: K3 as a warp-per-row march instead of the tile kernel
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
+    DevBuf pad_imgs, pad_ref;
+    Ad2Geom ad2;
+    uint64_t ad2_zero_key = 0;
+    bool use_ad2 = false;      // this frame's AD volume comes from k_ad_tile (all pair offsets within +-2) instead of the line-image gather
     ApGeom ap;
     uint64_t ap_zero_key = 0;  // geometry + buffer the zero borders of AP were last established for
     DevBuf staging_host;  // pinned host staging for image uploads / result downloads

@@ -73,6 +73,7 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
     if (const char* e = getenv("SVA_SGM_LPL")) c->tune_sgm_lpl = atoi(e);
     if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
+    if (const char* e = getenv("SVA_AD_GATHER")) c->tune_ad_gather = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE_WINDOW")) c->tune_sgm_pace_window = atoi(e);
     *out = c;
     return SVA_OK;
@@ -82,7 +83,7 @@ int sva_destroy(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
-    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
+    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->pad_imgs, &c->pad_ref, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
     if (c->staging_host.p) cudaFreeHost(c->staging_host.p);
