@@ -61,6 +61,8 @@ struct sva_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t aux_stream = nullptr;  // second stream for kernels that overlap with the main one (k_sgm.cu), forked / joined with the two events
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::string err;
     uint64_t launches = 0;
 
@@ -81,6 +83,8 @@ struct sva_ctx {
     int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
     int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
+    int tune_sgm_overlap = 0;     // SVA_SGM_OVERLAP (experiments, off): 1 = horizontal launch on a second stream next to the row-sweeping ones, 2 = up next to down.
+                                  // Measured on B200 at c1: no gain either way (1.53 ms per frame in all three) — the launches contend for the same issue slots / L2 REDs
     int tune_sgm_lpl = 32;        // SVA_SGM_LPL: lanes per path line in the accumulate passes (32 = one line per warp, 16 / 8 = two / four)
     int tune_ad_gather = 0;       // SVA_AD_GATHER=1: force the line-image gather AD kernel (k_ad.cu) even where the image-space kernel applies
     int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)
