@@ -140,7 +140,7 @@ __global__ void k_lr_check(const uint32_t* __restrict__ other_key, int W, int H,
 // a register rotation (the step loop is unrolled NV times) plus one shuffle for the lane edge; entries leaving the volume, and
 // everything still inside at the segment end, are merged into the global key map with atomicMin (segments are independent).
 // The integer scan is all this kernel does: validity, LR comparison and the parabola run once per pixel in k_wta_finish.
-#define WSEG_PF 6
+#define WSEG_PF 7  // ring of 8 stages: the slot index is s & 7
 
 template <int NV, int TDIR>
 __global__ void __launch_bounds__(256)
@@ -180,8 +180,8 @@ k_wta_seg(const uint16_t* __restrict__ S, int W, int H, int D, int dmin, int lr_
             if (s >= steps) break;
             cp_async_wait<WSEG_PF - 1>();
             uint32_t r[NR];
-            Vec<NR>::lds(ring + (s % NS) * STAGE, r);
-            if (s + WSEG_PF < len) Vec<NR>::cp_async(ring + ((s + WSEG_PF) % NS) * STAGE, src + (size_t)(s + WSEG_PF) * D);
+            Vec<NR>::lds(ring + (s & (NS - 1)) * STAGE, r);
+            if (s + WSEG_PF < len) Vec<NR>::cp_async(ring + ((s + WSEG_PF) & (NS - 1)) * STAGE, src + (size_t)(s + WSEG_PF) * D);
             cp_async_commit();
             const bool in = s < len;
             uint32_t key[NV];  // pixels past the segment end read as S = 0xFFFF (> any real S <= 65520): keys >= 0xFFFF0000 mean "no candidate"
