@@ -130,6 +130,17 @@ int sva_disparity_to_depth(sva_ctx* ctx, const sva_image_u8* disparity, double b
 int sva_depth_from_array(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others,
                          const sva_image_u8* mask, uint16_t* out_disp, float* out_subpix);
 
+/* Streaming form for a capture stream (configuration c4: independent frames): submit() returns at once with a ticket; frame t+1's
+ * upload overlaps frame t's kernels and frame t-1's download (two frames in flight, double-buffered inputs / outputs inside ctx).
+ * Every host buffer of a frame — images and outputs — must stay valid and untouched until sva_stream_wait(ticket) returns; use pinned
+ * memory for real overlap.  Results are identical to sva_depth_from_array. */
+int sva_stream_submit(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask,
+                      uint16_t* out_disp, float* out_subpix, int64_t* out_ticket);
+int sva_stream_wait(sva_ctx* ctx, int64_t ticket);
+/* device-clock stopwatch of the streaming path: elapsed(ticket) = time from the last mark() to the end of that frame's download */
+int sva_stream_mark(sva_ctx* ctx);
+int sva_stream_elapsed(sva_ctx* ctx, int64_t ticket, float* out_ms);
+
 /* ---- staged, device-resident form of the same pipeline (what bench.py times with inputs already in HBM) ------- */
 typedef enum sva_stage {
     SVA_STAGE_AD = 1,        /* K1a: A(y,x,d) = sum_k |R - I_k(shifted)|            -> u16 [H][W][D] */

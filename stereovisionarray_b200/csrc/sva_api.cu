@@ -1,4 +1,5 @@
 // sva_api.cu — extern "C" entry points of the volume-mode pipeline (staged / device-resident and host-buffer forms).
+#include <algorithm>
 #include <cstring>
 
 #include "sva_common.cuh"
@@ -257,6 +258,85 @@ int sva_depth_from_array(sva_ctx* c, const sva_params* p, const sva_image_u8* re
     SVA_TRY(sva_frame_upload(c, p, ref, others, mask));
     SVA_TRY(run_stage(c, SVA_STAGE_ALL));
     return sva_frame_download_disparity(c, out_disp, out_subpix);
+}
+
+/* ---- streaming form of sva_depth_from_array: a capture stream, two frames in flight ---------------------------------------------
+ * submit(t) uploads frame t on a copy stream, runs the stages on the compute stream and downloads the maps on a second copy stream;
+ * it returns at once.  Frame t+1's upload overlaps frame t's compute and frame t-1's download (two IoSets, swapped per frame).
+ * The host buffers (inputs and outputs) must stay valid until sva_stream_wait(ticket) returns; pin them for real overlap. */
+static void swap_io(sva_ctx* c) {
+    std::swap(c->pad_ref, c->alt.pad_ref); std::swap(c->pad_imgs, c->alt.pad_imgs); std::swap(c->ref_img, c->alt.ref_img);
+    std::swap(c->other_imgs, c->alt.other_imgs); std::swap(c->lines, c->alt.lines); std::swap(c->mask, c->alt.mask);
+    std::swap(c->disp, c->alt.disp); std::swap(c->subpix, c->alt.subpix); std::swap(c->ad2_zero_key, c->alt.ad2_zero_key);
+}
+
+static int stream_open(sva_ctx* c) {
+    if (c->h2d_stream) return SVA_OK;
+    SVA_CUDA_OK(c, cudaStreamCreateWithFlags(&c->h2d_stream, cudaStreamNonBlocking));
+    SVA_CUDA_OK(c, cudaStreamCreateWithFlags(&c->d2h_stream, cudaStreamNonBlocking));
+    SVA_CUDA_OK(c, cudaEventCreate(&c->ev_mark));
+    for (int i = 0; i < 2; i++) {
+        SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_h2d[i], cudaEventDisableTiming));
+        SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_compute[i], cudaEventDisableTiming));
+        SVA_CUDA_OK(c, cudaEventCreate(&c->ev_done[i]));
+    }
+    return SVA_OK;
+}
+
+int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask,
+                      uint16_t* out_disp, float* out_subpix, int64_t* out_ticket) {
+    if (!c || !out_disp || !out_ticket) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(stream_open(c));
+    const int64_t t = c->stream_ticket;
+    const int slot = (int)(t & 1);
+    if (t >= 2) SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[slot]));  // frame t-2 is out: its IoSet is free again
+    swap_io(c);
+    cudaStream_t compute = c->stream;
+    c->stream = c->h2d_stream;
+    int rc = sva_frame_upload(c, p, ref, others, mask);
+    c->stream = compute;
+    SVA_TRY(rc);
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_h2d[slot], c->h2d_stream));
+    SVA_CUDA_OK(c, cudaStreamWaitEvent(compute, c->ev_h2d[slot], 0));
+    SVA_TRY(run_stage(c, SVA_STAGE_ALL));
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_compute[slot], compute));
+    SVA_CUDA_OK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_compute[slot], 0));
+    const size_t px = (size_t)p->width * p->height;
+    SVA_CUDA_OK(c, cudaMemcpyAsync(out_disp, c->disp.p, px * 2, cudaMemcpyDeviceToHost, c->d2h_stream));
+    if (out_subpix) SVA_CUDA_OK(c, cudaMemcpyAsync(out_subpix, c->subpix.p, px * 4, cudaMemcpyDeviceToHost, c->d2h_stream));
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_done[slot], c->d2h_stream));
+    c->stream_ticket = t + 1;
+    *out_ticket = t;
+    return SVA_OK;
+}
+
+int sva_stream_wait(sva_ctx* c, int64_t ticket) {
+    if (!c || !c->h2d_stream) return SVA_ERR_BAD_ARG;
+    if (ticket < 0 || ticket >= c->stream_ticket) return c->fail(SVA_ERR_BAD_ARG, "unknown ticket");
+    if (ticket + 2 < c->stream_ticket) return SVA_OK;  // retired when its slot was reused
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[ticket & 1]));
+    return SVA_OK;
+}
+
+/* device-clock stopwatch of the streaming path: mark() stamps the upload stream, elapsed(ticket) is the time from the mark to the end of
+ * that frame's download (ticket must be one of the two most recent) */
+int sva_stream_mark(sva_ctx* c) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(stream_open(c));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->d2h_stream));
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_mark, c->h2d_stream));
+    return SVA_OK;
+}
+int sva_stream_elapsed(sva_ctx* c, int64_t ticket, float* out_ms) {
+    if (!c || !out_ms || !c->h2d_stream) return SVA_ERR_BAD_ARG;
+    if (ticket < 0 || ticket >= c->stream_ticket || ticket + 2 < c->stream_ticket) return c->fail(SVA_ERR_BAD_ARG, "ticket is not one of the two most recent");
+    SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[ticket & 1]));
+    SVA_CUDA_OK(c, cudaEventElapsedTime(out_ms, c->ev_mark, c->ev_done[ticket & 1]));
+    return SVA_OK;
 }
 
 }  // extern "C"

@@ -51,6 +51,14 @@ struct Ad2Geom {
     size_t img_bytes = 0;                      // bytes per padded other view
 };
 
+// The per-frame input / output buffers of a context.  The streaming entry points (sva_stream_*) keep two such sets and swap them
+// every frame, so frame t+1 uploads while frame t computes and frame t-1 downloads; the volumes (AP, C, S) are shared because the
+// compute stages of consecutive frames run back to back on one stream.
+struct IoSet {
+    DevBuf pad_ref, pad_imgs, ref_img, other_imgs, lines, mask, disp, subpix;
+    uint64_t ad2_zero_key = 0;
+};
+
 struct KernelTime {
     const char* name;
     cudaEvent_t beg, end;
@@ -63,6 +71,11 @@ struct sva_ctx {
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // second stream for kernels that overlap with the main one (k_sgm.cu), forked / joined with the two events
     cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    // ---- streaming pipeline (sva_stream_*) ----
+    cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_mark = nullptr;
+    IoSet alt;                 // the set not in use by the frame being submitted
+    int64_t stream_ticket = 0; // next ticket
     std::string err;
     uint64_t launches = 0;
 

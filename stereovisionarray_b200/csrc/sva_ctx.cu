@@ -87,6 +87,13 @@ int sva_destroy(sva_ctx* c) {
     DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->pad_imgs, &c->pad_ref, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
+    DevBuf* alts[] = {&c->alt.pad_ref, &c->alt.pad_imgs, &c->alt.ref_img, &c->alt.other_imgs, &c->alt.lines, &c->alt.mask, &c->alt.disp, &c->alt.subpix};
+    for (DevBuf* b : alts)
+        if (b->p) cudaFree(b->p);
+    if (c->h2d_stream) {
+        cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream); cudaEventDestroy(c->ev_mark);
+        for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_compute[i]); cudaEventDestroy(c->ev_done[i]); }
+    }
     if (c->staging_host.p) cudaFreeHost(c->staging_host.p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }

@@ -149,3 +149,28 @@ class DepthContext:
                                                      _p(disp, C.c_uint16), _p(sub, C.c_float)))
         self.params = p
         return disp, sub
+
+    # ---- capture stream: two frames in flight (upload of t+1 | kernels of t | download of t-1) ----
+    def stream_submit(self, p, ref, others, mask, disp, sub):
+        """enqueue one frame; every numpy buffer must stay alive and untouched until stream_wait(ticket) (pin them for real overlap)"""
+        r, rk = abi.image_u8(ref)
+        o, ok = abi.image_array(others) if not isinstance(others, tuple) else others
+        m = None
+        if mask is not None:
+            m, mk = abi.image_u8(mask)
+        t = C.c_int64()
+        check(self._h, self._L.sva_stream_submit(self._h, C.byref(p), C.byref(r), o, C.byref(m) if m is not None else None,
+                                                  _p(disp, C.c_uint16), _p(sub, C.c_float) if sub is not None else None, C.byref(t)))
+        self.params = p
+        return t.value
+
+    def stream_wait(self, ticket):
+        check(self._h, self._L.sva_stream_wait(self._h, C.c_int64(ticket)))
+
+    def stream_mark(self):
+        check(self._h, self._L.sva_stream_mark(self._h))
+
+    def stream_elapsed(self, ticket):
+        ms = C.c_float()
+        check(self._h, self._L.sva_stream_elapsed(self._h, C.c_int64(ticket), C.byref(ms)))
+        return ms.value

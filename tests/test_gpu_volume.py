@@ -78,6 +78,25 @@ def test_one_call_matches_oracle_pipeline(ctx, oracle):
     assert ctx.launches() > 0
 
 
+def test_stream_of_frames_matches_the_one_call_path(ctx, oracle):
+    """capture stream (c4): the double-buffered submit / wait pipeline returns, frame by frame, exactly what the one-call path returns"""
+    h, w, D = 80, 136, 64
+    p = abi.make_params(w, h, D, OFF8, win_half=4, n_paths=8, lr_gx=-1)
+    frames = [synth.make_scene(h, w, D, OFF8, 300 + i, face=(i % 2 == 0)) for i in range(5)]
+    outs = [(np.empty((h, w), np.uint16), np.empty((h, w), np.float32)) for _ in frames]
+    keep = [abi.image_array(f["others"]) for f in frames]
+    tickets = [ctx.stream_submit(p, f["ref"], k, f["mask"], o[0], o[1]) for f, k, o in zip(frames, keep, outs)]
+    assert tickets == sorted(tickets) and len(set(tickets)) == len(tickets)
+    for t in tickets:
+        ctx.stream_wait(t)
+    for f, o in zip(frames, outs):
+        disp_o, sub_o = oracle.depth_from_array(p, f["ref"], f["others"], f["mask"])
+        assert np.array_equal(o[0], disp_o) and np.array_equal(o[1], sub_o)
+    # and the context is still good for the one-call path afterwards
+    d1, s1 = ctx.depth_from_array(p, frames[0]["ref"], frames[0]["others"], frames[0]["mask"])
+    assert np.array_equal(d1, outs[0][0]) and np.array_equal(s1, outs[0][1])
+
+
 def test_pair_range_partials_sum_to_full(ctx, oracle):
     """what the pair-sharded multi-GPU reduce relies on: AD partials over disjoint pair ranges add up exactly"""
     h, w, D = 48, 64, 32
