@@ -219,6 +219,9 @@ def run_sva(args):
     sgm_bytes = (6 * p.n_paths - 4) * p.width * p.height * p.num_disp if p.n_paths else 0
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
                 "traffic": dom["traffic"], "peak_source": peak_src, "frac_of_8000": round(dom["achieved_gbs"] / 8000.0, 4),
+                # actual DRAM bytes (ncu) / event-timed duration: below `achieved` when L2 sharing moves fewer bytes than the algorithmic count
+                "dram_gbs": round(dom["traffic"] / dom["avg_ms"] / 1e6, 1) if dom["traffic"] else None,
+                "dram_frac": round(dom["traffic"] / dom["avg_ms"] / 1e6 / peak, 4) if dom["traffic"] else None,
                 "sgm_stage": {"algorithmic_bytes": sgm_bytes, "ms": round(sgm_ms, 4), "achieved_gbs": round(sgm_bytes / sgm_ms / 1e6, 1) if sgm_ms else None,
                               "frac": round(sgm_bytes / sgm_ms / 1e6 / peak, 4) if sgm_ms else None}}
     # ---- CPU baseline (rank 0, N = 1): the oracle port of the SAME pipeline on a bounded row band, all host cores ----
