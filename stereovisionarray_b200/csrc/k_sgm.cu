@@ -658,7 +658,9 @@ int sva_run_sgm(sva_ctx* ctx) {
             return SVA_OK;
         }
         // (zero-filling S from the box filter's store loop instead was measured: +0.06 ms there vs 0.05 ms for this memset)
-        SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.p, 0, cells * sizeof(uint16_t), ctx->stream));
+        if (ctx->s_prezeroed) SVA_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_zero, 0));  // zeroed next to K1a / K1b (sva_api.cu)
+        else SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.p, 0, cells * sizeof(uint16_t), ctx->stream));
+        ctx->s_prezeroed = false;
         if (ctx->tune_sgm_split && ctx->tune_sgm_lean && n == 8) {
             // variant C: two launches, each = the three directions sweeping the rows one way + one horizontal direction.  With a
             // balanced grid (same CTAs on every SM) the same-sweep directions advance in step without any explicit pacing, so the

@@ -92,6 +92,28 @@ int sva_frame_set_debug(sva_ctx* c, int32_t store_full_s, uint32_t sgm_dir_mask)
     return SVA_OK;
 }
 
+// Whole-frame runs zero the aggregation volume S on the second stream while K1a / K1b (bound by the integer pipe, not by HBM) run on
+// the main one; sva_run_sgm joins the event instead of issuing its own memset.
+static int prezero_s(sva_ctx* c) {
+    const sva_params& p = c->prm;
+    c->s_prezeroed = false;
+    if (p.n_paths == 0 || c->tune_sgm_fused_final || c->sgm_dir_mask_override || !c->tune_prezero) return SVA_OK;
+    const size_t bytes = (size_t)p.width * p.height * p.num_disp * sizeof(uint16_t);
+    SVA_TRY(c->reserve(c->S, bytes + 64));
+    if (!c->aux_stream) {
+        SVA_CUDA_OK(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
+        SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+        SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+    }
+    if (!c->ev_zero) SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));            // after the previous frame's last reader of S
+    SVA_CUDA_OK(c, cudaStreamWaitEvent(c->aux_stream, c->ev_fork, 0));
+    SVA_CUDA_OK(c, cudaMemsetAsync(c->S.p, 0, bytes, c->aux_stream));
+    SVA_CUDA_OK(c, cudaEventRecord(c->ev_zero, c->aux_stream));
+    c->s_prezeroed = true;
+    return SVA_OK;
+}
+
 static int run_stage(sva_ctx* c, int stage) {
     switch (stage) {
         case SVA_STAGE_AD:
@@ -104,6 +126,7 @@ static int run_stage(sva_ctx* c, int stage) {
             if (!c->have_cost) return c->fail(SVA_ERR_STATE, "cost volume not computed");
             return sva_run_sgm(c);
         case SVA_STAGE_ALL:
+            SVA_TRY(prezero_s(c));
             SVA_TRY(run_stage(c, SVA_STAGE_AD));
             SVA_TRY(run_stage(c, SVA_STAGE_BOX));
             return run_stage(c, SVA_STAGE_SGM);

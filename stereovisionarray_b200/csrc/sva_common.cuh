@@ -70,7 +70,9 @@ struct sva_ctx {
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
     cudaStream_t aux_stream = nullptr;  // second stream for kernels that overlap with the main one (k_sgm.cu), forked / joined with the two events
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_zero = nullptr;
+    bool s_prezeroed = false;  // S is being zeroed on aux_stream for the SGM of this whole-frame run (ev_zero marks the end)
+    int tune_prezero = 1;      // SVA_PREZERO: overlap the S memset with K1a / K1b
     // ---- streaming pipeline (sva_stream_*) ----
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_mark = nullptr;

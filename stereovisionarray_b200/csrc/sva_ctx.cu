@@ -73,6 +73,7 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
     if (const char* e = getenv("SVA_SGM_LPL")) c->tune_sgm_lpl = atoi(e);
     if (const char* e = getenv("SVA_SGM_OVERLAP")) c->tune_sgm_overlap = atoi(e);
+    if (const char* e = getenv("SVA_PREZERO")) c->tune_prezero = atoi(e);
     if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
     if (const char* e = getenv("SVA_AD_GATHER")) c->tune_ad_gather = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE_WINDOW")) c->tune_sgm_pace_window = atoi(e);
@@ -97,6 +98,7 @@ int sva_destroy(sva_ctx* c) {
     if (c->staging_host.p) cudaFreeHost(c->staging_host.p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+    if (c->ev_zero) cudaEventDestroy(c->ev_zero);
     cudaStreamDestroy(c->own_stream);
     delete c;
     return SVA_OK;
