@@ -466,7 +466,8 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines_all, size_t r
     int threads = warps * 32;
     bool n_vert = false;
     for (int i = 0; i < q.ndirs; i++) n_vert = n_vert || q.dys[i] != 0;
-    if (qq.balanced && qq.cta_sync && ctx->tune_sgm_pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
+    const bool pace = ctx->tune_sgm_pace < 0 ? (size_t)q.W * q.D * 4 >= 768 * 1024 : ctx->tune_sgm_pace != 0;
+    if (qq.balanced && qq.cta_sync && pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
         // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
         int per_sm = 0;
         SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, LPL>, threads + 32, smem));

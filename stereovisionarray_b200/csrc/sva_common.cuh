@@ -91,10 +91,11 @@ struct sva_ctx {
     int tune_sgm_concurrent = 1;  // SVA_SGM_CONCURRENT: run the RED-accumulating SGM directions in one launch
     int tune_sgm_fused_final = 0; // SVA_SGM_FUSED_FINAL: last path + K3 in one march (variant A) instead of all-RED + WTA march
     int tune_sgm_split = 2;       // SVA_SGM_SPLIT: 0 = one launch, 1 = two (down + right, up + left), 2 = three (down-sweeping, up-sweeping, horizontal; default), 3 = six row-sweeping + two horizontal
-    int tune_sgm_pace = 0;        // SVA_SGM_PACE (experimental, off): keep all CTAs of a launch within pace_window rounds of each other.
-                                  // Measured on B200 at c1: DRAM traffic per launch 2.74 -> 1.81 GB, but time 0.54 -> 0.62 ms (the grid then moves at the
-                                  // pace of its slowest CTA and becomes issue/barrier-bound), so it is not the default.
-    int tune_sgm_pace_window = 4; // SVA_SGM_PACE_WINDOW: rounds of 9 rows
+    int tune_sgm_pace = -1;       // SVA_SGM_PACE: keep all CTAs of a row-sweeping launch within pace_window rounds (of 9 rows) of each other.
+                                  // -1 = automatic: on when one image row of C + S (W*D*4 bytes) is 768 KB or more.  The three directions of such a
+                                  // launch share C and S lines in L2 only while their rows stay within the L2-resident window; unpaced drift is harmless
+                                  // at c1 (0.66 MB per row: 0.277 ms unpaced, 0.283 paced) and costly at c4 (1.47 MB per row: 1.355 -> 0.925 ms paced).
+    int tune_sgm_pace_window = 2; // SVA_SGM_PACE_WINDOW: rounds of 9 rows
     int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
     int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
