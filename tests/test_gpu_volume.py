@@ -29,6 +29,8 @@ CASES = [
     (50, 70, 96, [(-1, 0), (0, 1)], dict(win_half=13, n_paths=0, lr_gx=-1)),
     (40, 611, 40, OFF8, dict(win_half=7, n_paths=4, lr_gx=-1)),   # several 256-column box strips, win_half % 4 != 0, D % 16 != 0, ragged width
     (150, 300, 24, [(1, 0), (0, -1), (-1, 1)], dict(win_half=9, n_paths=8, lr_gx=1, min_disp=2)),  # several row bands
+    (90, 200, 16, [(3, 0), (-3, 1), (1, -4)], dict(win_half=3, n_paths=4, lr_gx=-1)),  # pair offsets beyond +-2: the line-image gather AD kernel
+    (48, 260, 64, [(2, -2), (-2, 2), (0, 2), (2, 0)], dict(win_half=4, n_paths=8, lr_gx=1, min_disp=5)),  # |g| = 2 bodies of the image-space AD kernel, min_disp % 4 != 0
 ]
 
 
