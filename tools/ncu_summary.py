@@ -7,7 +7,11 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__throughput.avg.pct_of_peak_sustained_elapsed", "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed",
         "launch__registers_per_thread", "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "sm__warps_active.avg.pct_of_peak_sustained_active",
         "smsp__issue_active.avg.pct_of_peak_sustained_active", "smsp__inst_executed.sum", "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
-        "smsp__average_warp_latency_per_inst_issued.ratio"]
+        "smsp__average_warp_latency_per_inst_issued.ratio",
+        # issue utilisation per execution pipe (ALU = integer / DPX min-max pipe, FMA = IMAD pipe, LSU = shared / global / shuffle)
+        "sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active", "sm__inst_executed_pipe_uniform.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_cbu.avg.pct_of_peak_sustained_active"]
 STALL = "smsp__average_warps_issue_stalled_"
 
 
