@@ -1,4 +1,6 @@
-// k_ad.cu — K1a: per-pixel absolute-difference volume summed over camera pairs.
+// k_ad.cu — K1a, line-image gather form: per-pixel absolute-difference volume summed over camera pairs, for ANY integer pair
+// offsets.  The volume pipeline uses the image-space kernel of k_ad2.cu whenever every |gx|,|gy| <= 2 (all BASELINE grids) and
+// this one otherwise; the planar output layout (ApGeom), its allocation and the unpack kernel live here.
 //
 //   A(y,x,d) = sum_k |R(y,x) - I_k(y - gy_k*delta, x - gx_k*delta)|,  delta = min_disp + d      (u16; stored planar, see ApGeom)
 //

@@ -3,7 +3,9 @@
 //   C_raw(y,x,d) = sum_{j,i in [-k,k)} A(y+j, x+i, d)            (half-open window — reference src/CameraStereoVision.cpp:57,77)
 //   PACK_U16: C = valid ? min(cap, C_raw >> shift) : cap           RAW_U32: C = valid ? C_raw : 0xFFFFFFFF
 //
-// A CTA owns a strip of TXi = 16*NC columns x 32 disparities and marches down a band of rows.  Each thread keeps the
+// Two kernels: k_box_planar (below, the volume pipeline's hot path, reads the planar AD volume) and the general k_box_cost
+// ([H][W][D] u16 in, PACK_U16 or RAW_U32 out; literal mode, improveWithDisparity and the RAW recomputation use it):
+// A CTA of k_box_cost owns a strip of TXi = 16*NC columns x 32 disparities and marches down a band of rows.  Each thread keeps the
 // vertical running sums V of NC consecutive columns x 2 disparities in registers (add the row entering the window,
 // subtract the row leaving it).  The horizontal window sum is a difference of row prefix sums: every thread scans its
 // own NC columns in registers, segment totals are exchanged through shared memory, and the prefix row P lives in

@@ -1,4 +1,5 @@
-// k_sgm.cu — K2: semi-global path aggregation; K3 (WTA + left-right check + parabolic sub-pixel) fused into the last pass.
+// k_sgm.cu — K2: semi-global path aggregation (K3 — WTA / left-right check / sub-pixel — follows in k_wta.cu; the fused
+// last-pass form is kept as variant A).
 //
 // No counterpart in the reference: this implements the frozen spec of DESIGN.md §3.3 (Hirschmueller 2008,
 // fixed P1/P2), bit-exact against oracle/sva_oracle.c.
@@ -8,17 +9,20 @@
 //
 // Mapping: ONE WARP PER PATH LINE per direction.  A lane owns n = 2*NR consecutive disparities packed two per register
 // (u16x2); the recurrence is DPX (VIADDMNMX.U16x2 / VIMNMX.U16x2), the d-1 / d+1 neighbours are one PRMT per register plus
-// two warp shuffles for the lane edges, and min_k is a per-lane VIMNMX tree followed by one REDUX.MIN.  Everything stays in
-// registers along the path; C is streamed with a PF-deep register prefetch ring (L1::no_allocate), S is accumulated with
-// fire-and-forget 64-bit REDs (packed u16x4 adds are carry-free by the bound above), stored plainly by the first pass and
-// only read by the last pass.  Diagonal paths use W lines of exactly H steps that wrap around the image edge and restart
-// (L = C) where the predecessor is outside the image, so every pass has uniform work per warp.
+// two warp shuffles for the lane edges, and min_k is a VIMNMX3 fold followed by one CREDUX.MIN.  Everything stays in
+// registers along the path; C is streamed by cp.async (LDGSTS) into a per-warp ring of PF + 1 shared-memory stages, S is
+// accumulated with fire-and-forget 64-bit REDs (packed u16x4 adds are carry-free by the bound above) into a zeroed volume.
+// Diagonal paths use W lines of exactly H steps that wrap around the image edge and restart (L = C) where the predecessor
+// is outside the image, so every line of a launch has the same length.
 //
-// Last pass (horizontal): S_total = S + L in registers -> packed (S<<16|d) keys -> REDUX.MIN gives the first-minimum
-// winner; S(d*-1), S(d*+1) are fetched with two shuffles for the parabola; the other view's WTA (left-right check) is a
-// systolic diagonal minimum: one key register per disparity slot shifts by one slot per step (one shuffle per step), so
-// D_o(x') = argmin_d S(y, x'+lr_gx*delta, d) falls out of the same march with no extra memory traffic.  Results of a row
-// are staged in shared memory and written coalesced by a row-end sweep that applies mask / border / cell-validity / LR.
+// Default schedule for 8 paths (sva_run_sgm, variant D): three launches — the three directions that sweep the rows
+// downwards, the three that sweep upwards, the two horizontal ones.  All lines of a row-sweeping launch advance one row per
+// step, so a row's C and S lines are touched by all three directions while they are L2-resident (DRAM sees C once and S once
+// per launch); when an image row of C + S is 768 KB or more the CTAs are additionally paced against the grid-wide minimum.
+//
+// Variant A's last pass (k_sgm_pass<FINAL>, horizontal): S_total = S + L in registers -> packed (S<<16|d) keys -> REDUX.MIN
+// gives the first-minimum winner; S(d*-1), S(d*+1) are fetched with two shuffles for the parabola; the other view's WTA
+// (left-right check) is a systolic diagonal minimum: one key register per disparity slot shifts by one slot per step.
 #include <algorithm>
 #include <cstdlib>
 
