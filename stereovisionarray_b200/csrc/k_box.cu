@@ -370,9 +370,12 @@ static int sva_launch_box_planar(sva_ctx* ctx) {
     }
     q.txo = ctx->ap.txo; q.wp = ctx->ap.wp; q.row_words = (long long)ctx->ap.row_words;
     const int strips = ctx->ap.strips, dgroups = div_up(D, 16);
-    // Row bands: every band re-reads 2k-1 warm-up rows, and the grid should fill whole waves of 2 CTAs per SM.  Pick the band
+    // Row bands: every band re-reads 2k-1 warm-up rows, and the grid should fill whole waves of the resident CTAs.  Pick the band
     // count that minimises waves x rows marched per CTA.
-    const int slots = 2 * ctx->sm_count, per_band = strips * dgroups;
+    int per_sm = 2;
+    SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_box_planar, 256, 0));
+    if (per_sm < 1) per_sm = 1;
+    const int slots = per_sm * ctx->sm_count, per_band = strips * dgroups;
     int bands = 1;
     double best = 1e30;
     for (int b = 1; b <= H && b <= 4096; b++) {
