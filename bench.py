@@ -240,6 +240,12 @@ def run_sva(args):
             best = min(best, time.perf_counter() - t0)
         cpu = {"value": round(p.width * band * p.num_disp / 1e6 / best, 2), "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port",
                "sample": "oracle/sva_oracle.c volume pipeline (OpenMP) on a %dx%d row band of the %s frame, D=%d, %d pairs, best of 3" % (p.width, band, name, p.num_disp, p.n_pairs)}
+    literal = None
+    if world == 1 and not args.no_cpu:
+        try:
+            literal = literal_mode_line(p.width, p.height)
+        except Exception as ex:  # reported, never fatal for the headline line
+            literal = {"error": str(ex)[:200]}
     out = {
         "metric": "MDE/s", "value": round(value, 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if batch > 1 else "weak", "vs_baseline": None, "dtype": "u16",
@@ -251,7 +257,7 @@ def run_sva(args):
         "e2e": {"value": round(e2e_value, 1), "unit": "MDE/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                 "api": "sva_stream_submit / sva_stream_wait (C ABI, pinned host buffers, two frames in flight)",
                 "single_call_ms_per_step": round(single_ms / args.steps, 4), "single_call_api": "sva_depth_from_array, one synchronous call per frame"},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "clocks": clocks, "kernels": rows,
+        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "literal_mode": literal, "clocks": clocks, "kernels": rows,
     }
     emit(json.dumps(out))
     if use_dist:
@@ -352,21 +358,47 @@ def _ref_band_worker(job):
         dt = time.perf_counter() - t0
     finally:
         os.dup2(saved, 1); os.close(devnull); os.close(saved)
-    # count the candidates the loop nest evaluated (geometry only)
+    return dt, literal_evals(w, band)
+
+
+def literal_evals(w, h, stride=16):
+    """pixel x candidate evaluations of the reference's loop nest for pair {12,11} on a w x h frame (geometry only; every `stride`-th
+    column is walked and scaled)"""
+    from oracle.oracle import Oracle
     o = Oracle()
     cams = [abi.camera(*c) for c in synth.reference_cameras(w)]
-    hx, hy = w // 2, band // 2
+    hx, hy = w // 2, h // 2
     evals = 0
-    for y in range(20, band - 20):
-        for x in range(20, w - 20, 16):  # sampled every 16th column, scaled
+    for y in range(20, h - 20):
+        for x in range(20, w - 20, stride):
             ray = o.camera_inv_project(cams[12], (x - hx, y - hy))
             a = o.camera_project(cams[11], [cams[12].pos[i] + ray[i] * 0.5 for i in range(3)])
             b = o.camera_project(cams[11], [cams[12].pos[i] + ray[i] * 1.0 for i in range(3)])
             a, b = (a[0] + hx, a[1] + hy), (b[0] + hx, b[1] + hy)
-            if min(a[0], b[0]) < 20 or max(a[0], b[0]) > w - 20 or min(a[1], b[1]) < 20 or max(a[1], b[1]) > band - 20:
+            if min(a[0], b[0]) < 20 or max(a[0], b[0]) > w - 20 or min(a[1], b[1]) < 20 or max(a[1], b[1]) > h - 20:
                 continue
-            evals += 16 * (max(abs(a[0] - b[0]), abs(a[1] - b[1])) + 1)
-    return dt, evals
+            evals += stride * (max(abs(a[0] - b[0]), abs(a[1] - b[1])) + 1)
+    return evals
+
+
+def literal_mode_line(w, h, reps=5):
+    """the reference's OWN algorithm (SAD 40x40 over the Bresenham candidates, first-min WTA, improveWithDisparity) on the GPU through the
+    C ABI, whole w x h frame, host buffers in and out — the like-for-like counterpart of `--impl reference` (same MDE definition)"""
+    from stereovisionarray_b200 import reference_api as api
+    sc = synth.make_literal_scene(h, w, 7000)
+    cams = [api.Camera(f, pos, ps) for pos, f, ps in synth.reference_cameras(w)]
+    mask = np.zeros((h, w), np.uint8)
+    mask[20:h - 20, 20:w - 20] = 255
+    run = lambda: api.improveWithDisparity(api.matchLiteral(sc["images"], cams, [(12, 11)], mask, 20, 0.5, 1.0), sc["images"][12], [sc["images"][11]],
+                                           [(cams[12], cams[11])], 21, mask)
+    run()
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        run()
+    dt = (time.perf_counter() - t0) / reps
+    ev = literal_evals(w, h, stride=64)
+    return {"ms_per_frame": round(dt * 1e3, 3), "value": round(ev / 1e6 / dt, 1), "unit": "MDE/s (pixel x candidate evaluations, as --impl reference)",
+            "api": "sva_match_literal + sva_improve_with_disparity (host buffers, wall clock)", "frame": "%dx%d, pair {12,11}, mask = interior" % (w, h)}
 
 
 def run_reference(args):

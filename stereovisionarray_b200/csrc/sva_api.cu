@@ -313,6 +313,13 @@ int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, 
     SVA_TRY(stream_open(c));
     const int64_t t = c->stream_ticket;
     const int slot = (int)(t & 1);
+    if (t > 0 && p && (p->width != c->prm.width || p->height != c->prm.height || p->num_disp != c->prm.num_disp || p->n_pairs != c->prm.n_pairs ||
+                       p->win_half != c->prm.win_half || p->min_disp != c->prm.min_disp)) {
+        // a different geometry re-allocates workspaces: drain the pipeline first so no frame in flight still uses the old ones
+        SVA_CUDA_OK(c, cudaStreamSynchronize(c->h2d_stream));
+        SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+        SVA_CUDA_OK(c, cudaStreamSynchronize(c->d2h_stream));
+    }
     if (t >= 2) SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[slot]));  // frame t-2 is out: its IoSet is free again
     swap_io(c);
     cudaStream_t compute = c->stream;

@@ -85,6 +85,8 @@ int sva_destroy(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
+    if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(c->d2h_stream); }
     DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->pad_imgs, &c->pad_ref, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
     for (DevBuf* b : bufs)
         if (b->p) cudaFree(b->p);
