@@ -281,11 +281,19 @@ def run_pair_sharded(args, rank, local_rank, world):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
-    ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
-    ptr, nbytes = ctx.ad_device_ptr()
-    vol = torch.as_tensor(sdist._CudaAlias(ptr, nbytes // 4), device="cuda")
+    slices = args.c3_scheme == "slices"
+    keep = {}
+    if slices:
+        ctx.upload(sdist.slice_params(p, rank, world), sc["ref"], sc["others"], sc["mask"])
+    else:
+        ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+        ptr, nbytes = ctx.ad_device_ptr()
+        vol = torch.as_tensor(sdist._CudaAlias(ptr, nbytes // 4), device="cuda")
 
     def step():
+        if slices:
+            sdist.slice_sharded_compute(ctx, p, rank, world, None, keep)
+            return
         if e > b:
             ctx.set_pair_range(b, e)
             ctx.run(abi.STAGE_AD)
@@ -329,8 +337,10 @@ def run_pair_sharded(args, rank, local_rank, world):
                "frames_per_s": round(args.steps / (ms / 1e3), 3),
                "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": p.n_pairs + 1,
                           "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths,
-                          "partitioning": "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9),
-                          "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (nbytes / 1e6)},
+                          "partitioning": ("disparity slices of %d (cost volume, no reduction) -> all-gather -> path directions %s -> reduce-scatter by row blocks -> "
+                                           "row-sharded WTA; %d ranks" % (p.num_disp // world, sdist.direction_masks(p.n_paths, world), world)) if slices else
+                                          "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9),
+                          "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
                "e2e": None, "gpu_launches": int(launches), "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "note": "see the c1 line for per-kernel rooflines"},
                "cpu_baseline": None, "clocks": clocks}
         emit(json.dumps(out))
@@ -471,6 +481,8 @@ def main():
     ap.add_argument("--cpu-band", type=int, default=256, help="rows of the CPU-baseline sample")
     ap.add_argument("--ref-band", type=int, default=44, help="rows per band of the reference arm (40 + valid rows)")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--c3-scheme", default="slices", choices=["pairs", "slices"],
+                    help="c3 only: 'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding (DESIGN.md §7)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "sva" else args.warmup
     with StdoutToStderr():

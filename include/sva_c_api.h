@@ -176,6 +176,20 @@ int sva_frame_download_disparity(sva_ctx* ctx, uint16_t* out_disp, float* out_su
 /* Device pointer + byte size of the A volume, so a caller can reduce it across GPUs (NCCL via torch.distributed). */
 int sva_frame_ad_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);
 
+/* ---- multi-GPU building blocks for ONE frame sharded by disparity slices, path directions and row blocks ----------
+ * Rank r of G uploads the frame with num_disp = D/G and min_disp = dmin + r*D/G and runs SVA_STAGE_AD + SVA_STAGE_BOX: that is its slice of
+ * the cost volume, complete, with no cross-GPU reduction.  The caller all-gathers the slices into a slice-major device volume
+ * [G][H][W][D/G], switches every rank to the full range with sva_frame_set_params, lets each rank aggregate its share of the path directions
+ * (sva_frame_sgm_directions: the result is that rank's partial S over `rows_alloc` >= H rows, rows beyond H zero), reduce-scatters the
+ * partial sums by row blocks and runs K3 per block (sva_frame_wta_rows; the left-right check is row-local). */
+int sva_frame_cost_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);  /* C [H][W][D] of the current parameters */
+int sva_frame_set_params(sva_ctx* ctx, const sva_params* p);                      /* same images and mask, new disparity range / SGM parameters */
+/* dir_mask bit i = direction i of {v+, v-, h+, h-, d++, d-+, d+-, d--}; slice_disp = D/G for a slice-major volume, 0 for [H][W][D] */
+int sva_frame_sgm_directions(sva_ctx* ctx, const void* cost_dev, int32_t slice_disp, uint32_t dir_mask, int32_t rows_alloc, void** out_s_ptr,
+                             size_t* out_bytes);
+int sva_frame_wta_rows(sva_ctx* ctx, const void* s_rows_dev, int32_t y0, int32_t rows);  /* s_rows_dev = image rows [y0, y0+rows) of S */
+int sva_frame_download_disparity_rows(sva_ctx* ctx, int32_t rows, uint16_t* out_disp, float* out_subpix);
+
 #ifdef __cplusplus
 }
 #endif

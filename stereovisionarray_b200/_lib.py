@@ -18,6 +18,7 @@ EXPORTS = [
     "sva_frame_upload", "sva_frame_set_pair_range", "sva_frame_run", "sva_frame_time", "sva_frame_kernel_times", "sva_frame_time_detailed", "sva_timer_start", "sva_timer_stop", "sva_frame_set_debug",
     "sva_frame_download_ad", "sva_frame_download_cost", "sva_frame_download_raw_cost", "sva_frame_download_sgm",
     "sva_frame_download_disparity", "sva_frame_ad_device_ptr", "sva_frame_mark_ad_ready",
+    "sva_frame_cost_device_ptr", "sva_frame_set_params", "sva_frame_sgm_directions", "sva_frame_wta_rows", "sva_frame_download_disparity_rows",
 ]
 
 _lib = None

@@ -53,6 +53,7 @@ struct SgmParams {
     unsigned int* pace_arrive;  // k_sgm_acc: [pace_rounds] CTAs that finished round r (nullptr = no global pacing)
     unsigned int* pace_min;     // rounds finished by every CTA
     int pace_rounds, pace_window, march_warps;
+    int c_ds;           // 0: C is [H][W][D]; > 0: C is slice-major [D / c_ds][H][W][c_ds] (disparity slices gathered from several GPUs)
     int exp_no_out;     // timing experiment only (SVA_SGM_EXP=1): run the recurrence but drop the S updates
     int cta_sync;       // k_sgm_acc (balanced): named barrier among the row-sweeping warps of a CTA every round
     int balanced;       // k_sgm_acc: grid = m * SM count; warp w of CTA b handles direction w % ndirs, line b + grid * (w / ndirs)
@@ -331,20 +332,24 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
     const int lin = lane % LPL;  // lane within this line's group (LPL lanes per line, 32 / LPL lines per warp)
     const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lin * NV);
-    uint32_t ic = start, is = start;                  // prefetch cursor (C), accumulate cursor (S)
+    // the cost volume may be slice-major (a lane's cells never straddle a slice: c_ds % NV == 0): same walk, pixel stride c_ds
+    const int cds = q.c_ds > 0 ? q.c_ds : D;
+    const uint32_t dstep_c = (uint32_t)((dy * W + dx) * cds), wrapfix_c = (uint32_t)(-dx * W * cds);
+    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lin * NV) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lin * NV) % cds) : start;
+    uint32_t ic = start_c, is = start;                // prefetch cursor (C), accumulate cursor (S)
     int cc = dx > 0 ? W - x0 : x0 + 1, cs = cc;       // steps until each cursor leaves the image sideways
     const bool active = FULL || lin < q.lanes;
     const bool first_lane = lin == 0, last_lane = FULL ? lin == LPL - 1 : lin == q.lanes - 1;
-    auto adv = [&](uint32_t& i, int& cnt) -> bool {
-        i += dstep;
+    auto adv = [&](uint32_t& i, int& cnt, const uint32_t step, const uint32_t fix) -> bool {
+        i += step;
         if (DIAG) {
-            if (--cnt == 0) { cnt = W; i += wrapfix; return true; }
+            if (--cnt == 0) { cnt = W; i += fix; return true; }
         }
         return false;
     };
 #pragma unroll
     for (int u = 0; u < PF; u++) {
-        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc); }
+        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
         cp_async_commit();
     }
     uint32_t L[NR];
@@ -358,7 +363,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
 #pragma unroll
         for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
         if (active) Vec<NR>::lds(slot_addr, Cc);
-        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); adv(ic, cc); }
+        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
         cp_async_commit();
         if (DIAG && restart) {
 #pragma unroll
@@ -367,7 +372,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
         }
         sgm_step<NR, LPL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
         if (active && do_out) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
-        restart = adv(is, cs);
+        restart = adv(is, cs, dstep, wrapfix);
     };
     int s0 = 0;
     for (; s0 + NS + PF <= len; s0 += NS) {
@@ -595,6 +600,42 @@ int sva_sgm_regs_per_lane(int D) {
 // Pass order (oracle direction indices in ORC_DIRS order: 0 v+, 1 v-, 2 h+, 3 h-, 4..7 diagonals):
 //   8 paths: 0 (store), 1, 4, 5, 6, 7, 2 (RED), 3 (final)     4 paths: 0 (store), 1, 2 (RED), 3 (final)
 static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+
+// Selected path directions on an EXTERNAL cost volume, optionally slice-major (multi-GPU: every rank gathers all disparity slices and
+// aggregates its share of the directions; the partial sums are then reduce-scattered by rows).  The first direction stores, the others
+// RED, so ctx->S ends up as the sum of exactly these directions.  bit i = direction i of {v+, v-, h+, h-, d++, d-+, d+-, d--}.
+int sva_run_sgm_dirs(sva_ctx* ctx, const uint16_t* Cext, int c_ds, uint32_t dir_mask, int rows_alloc) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp;
+    const int nr = sva_sgm_regs_per_lane(D);
+    if (nr == 0) return ctx->fail(SVA_ERR_BAD_ARG, "unsupported num_disp");
+    if (c_ds > 0 && (D % c_ds || c_ds % (2 * nr))) return ctx->fail(SVA_ERR_BAD_ARG, "slice size must divide num_disp and hold whole lanes");
+    if (!(dir_mask & 0xFFu)) return ctx->fail(SVA_ERR_BAD_ARG, "empty direction mask");
+    if (rows_alloc < H) rows_alloc = H;
+    const size_t cells = (size_t)W * rows_alloc * D;
+    SVA_TRY(ctx->reserve(ctx->S, cells * sizeof(uint16_t) + 64));
+    if (rows_alloc > H)  // padding rows (the reduce-scatter wants equal row blocks) must read as zero
+        SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.as<uint16_t>() + (size_t)W * H * D, 0, (size_t)W * (rows_alloc - H) * D * sizeof(uint16_t), ctx->stream));
+    SgmParams q{};
+    q.C = Cext; q.S = ctx->S.as<uint16_t>(); q.W = W; q.H = H; q.D = D; q.c_ds = c_ds;
+    q.p1p1 = (uint32_t)p.p1 * 0x10001u; q.p2p2 = (uint32_t)p.p2 * 0x10001u;
+    q.lanes = D / (2 * nr);
+    static const int DIRS8[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}, {1, -1}, {-1, -1}};
+    const int lean = ctx->tune_sgm_lean, lpl = ctx->tune_sgm_lpl;
+    ctx->tune_sgm_lean = 1; ctx->tune_sgm_lpl = 32;  // the slice-major cursor lives in the lean one-line-per-warp march
+    bool first = true;
+    int rc = SVA_OK;
+    for (int i = 0; i < 8 && rc == SVA_OK; i++) {
+        if (!(dir_mask & (1u << i))) continue;
+        q.ndirs = 1; q.dxs[0] = DIRS8[i][0]; q.dys[0] = DIRS8[i][1];
+        rc = launch_pass_nr(ctx, q, nr, first ? SGM_MODE_STORE : SGM_MODE_RED);
+        first = false;
+    }
+    ctx->tune_sgm_lean = lean; ctx->tune_sgm_lpl = lpl;
+    SVA_TRY(rc);
+    ctx->have_sgm = true;
+    return SVA_OK;
+}
 
 int sva_run_sgm(sva_ctx* ctx) {
     const sva_params& p = ctx->prm;

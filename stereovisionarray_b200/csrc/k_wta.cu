@@ -23,6 +23,7 @@ struct WtaParams {
     int gxp, gxn, gyp, gyn;
     int lr_gx, lr_max_diff, subpixel;
     int stride_w;  // padded pixel stride in 32-bit words
+    int y0, Hfull; // the volume holds image rows [y0, y0 + H) of an image Hfull rows high (row-sharded WTA); whole image: 0, H
     const uint8_t* mask;
     uint16_t* disp;
     float* sub;
@@ -71,14 +72,15 @@ k_wta_tile(WtaParams q) {
                 const int den = sl - 2 * s0 + sr;
                 if (den > 0) f = (float)d + (float)(sl - sr) / (float)(2 * den);
             }
-            bool ok = x >= k && x < W - k && y >= k && y < H - k;
-            if (ok && q.mask) ok = q.mask[(size_t)y * W + x] != 0;
+            const int yy = y + q.y0, HH = q.Hfull;  // image row (the volume may be a row block)
+            bool ok = x >= k && x < W - k && yy >= k && yy < HH - k;
+            if (ok && q.mask) ok = q.mask[(size_t)yy * W + x] != 0;
             if (ok) {
                 int lim = 0x7FFFFFFF;
                 if (q.gxp > 0) lim = min(lim, (x - k) / q.gxp);
                 if (q.gxn > 0) lim = min(lim, (W - k - x) / q.gxn);
-                if (q.gyp > 0) lim = min(lim, (y - k) / q.gyp);
-                if (q.gyn > 0) lim = min(lim, (H - k - y) / q.gyn);
+                if (q.gyp > 0) lim = min(lim, (yy - k) / q.gyp);
+                if (q.gyn > 0) lim = min(lim, (HH - k - yy) / q.gyn);
                 ok = delta <= lim;
             }
             s_d[px] = ok ? (uint16_t)delta : (uint16_t)SVA_DISP_INVALID;
@@ -250,14 +252,15 @@ __global__ void k_wta_finish(const uint16_t* __restrict__ S, const uint16_t* __r
     if (x >= W) return;
     const size_t i = (size_t)y * W + x;
     const int d = dwin[i], delta = q.dmin + d;
-    bool ok = x >= k && x < W - k && y >= k && y < H - k;
-    if (ok && q.mask) ok = q.mask[i] != 0;
+    const int yy = y + q.y0, HH = q.Hfull;  // image row (the volume may be a row block)
+    bool ok = x >= k && x < W - k && yy >= k && yy < HH - k;
+    if (ok && q.mask) ok = q.mask[(size_t)yy * W + x] != 0;
     if (ok) {
         int lim = 0x7FFFFFFF;
         if (q.gxp > 0) lim = min(lim, (x - k) / q.gxp);
         if (q.gxn > 0) lim = min(lim, (W - k - x) / q.gxn);
-        if (q.gyp > 0) lim = min(lim, (y - k) / q.gyp);
-        if (q.gyn > 0) lim = min(lim, (H - k - y) / q.gyn);
+        if (q.gyp > 0) lim = min(lim, (yy - k) / q.gyp);
+        if (q.gyn > 0) lim = min(lim, (HH - k - yy) / q.gyn);
         ok = delta <= lim;
     }
     if (ok && q.lr_gx != 0) {
@@ -294,11 +297,19 @@ static cudaError_t wta_seg_launch(sva_ctx* ctx, const uint16_t* vol, const WtaPa
 }
 
 // vol = S_total (or C when there is no aggregation); fills ctx->disp / ctx->subpix
-int sva_run_wta(sva_ctx* ctx, const uint16_t* vol) {
+int sva_run_wta_rows(sva_ctx* ctx, const uint16_t* vol, int y0, int rows);
+int sva_run_wta(sva_ctx* ctx, const uint16_t* vol) { return sva_run_wta_rows(ctx, vol, 0, ctx->prm.height); }
+
+// K3 on a block of `rows` image rows starting at y0 (vol = those rows of the aggregated volume); results go to the first `rows` rows of
+// ctx->disp / ctx->subpix.  The left-right check is row-local, so row blocks are independent (row-sharded multi-GPU WTA).
+int sva_run_wta_rows(sva_ctx* ctx, const uint16_t* vol, int y0, int rows) {
     const sva_params& p = ctx->prm;
-    const int W = p.width, H = p.height, D = p.num_disp;
+    const int W = p.width, H = rows, D = p.num_disp;
+    if (y0 < 0 || rows < 1 || y0 + rows > p.height) return ctx->fail(SVA_ERR_BAD_ARG, "row block outside the image");
+    SVA_TRY(ctx->reserve(ctx->disp, (size_t)W * p.height * sizeof(uint16_t)));
+    SVA_TRY(ctx->reserve(ctx->subpix, (size_t)W * p.height * sizeof(float)));
     WtaParams q{};
-    q.S = vol; q.W = W; q.H = H; q.D = D; q.dmin = p.min_disp; q.k = p.win_half;
+    q.S = vol; q.W = W; q.H = H; q.D = D; q.dmin = p.min_disp; q.k = p.win_half; q.y0 = y0; q.Hfull = p.height;
     q.lr_gx = p.lr_gx; q.lr_max_diff = p.lr_max_diff; q.subpixel = p.subpixel;
     for (int i = 0; i < p.n_pairs; i++) {
         int gx = p.pair_gx[i], gy = p.pair_gy[i];

@@ -14,6 +14,8 @@ bool sva_ad2_usable(const sva_params& p);
 int sva_ad2_prepare(sva_ctx* ctx);
 uint8_t* sva_ad2_view_origin(sva_ctx* ctx, int k);
 int sva_run_ad2(sva_ctx* ctx);
+int sva_run_sgm_dirs(sva_ctx* ctx, const uint16_t* Cext, int c_ds, uint32_t dir_mask, int rows_alloc);
+int sva_run_wta_rows(sva_ctx* ctx, const uint16_t* vol, int y0, int rows);
 int sva_ap_unpack(sva_ctx* ctx);
 
 static int check_params(sva_ctx* c, const sva_params* p) {
@@ -281,6 +283,60 @@ int sva_depth_from_array(sva_ctx* c, const sva_params* p, const sva_image_u8* re
     SVA_TRY(sva_frame_upload(c, p, ref, others, mask));
     SVA_TRY(run_stage(c, SVA_STAGE_ALL));
     return sva_frame_download_disparity(c, out_disp, out_subpix);
+}
+
+/* ---- multi-GPU building blocks: disparity-slice / direction / row sharding of ONE frame ----------------------------
+ * rank r uploads the frame with num_disp = D/G, min_disp = dmin + r*D/G and runs STAGE_AD + STAGE_BOX: its slice of the cost volume
+ * (no cross-GPU reduction at all).  The slices are all-gathered into a slice-major volume [G][H][W][D/G]; every rank switches to the full
+ * disparity range (sva_frame_set_params), aggregates ITS directions on the gathered volume (sva_frame_sgm_directions) and the partial
+ * sums are reduce-scattered by row blocks; each rank then runs K3 on its rows (sva_frame_wta_rows). */
+int sva_frame_cost_device_ptr(sva_ctx* c, void** out_ptr, size_t* out_bytes) {
+    if (!c || !out_ptr || !out_bytes) return SVA_ERR_BAD_ARG;
+    if (!c->have_cost) return c->fail(SVA_ERR_STATE, "cost volume not computed");
+    *out_ptr = c->C.p; *out_bytes = cells(c) * 2;
+    return SVA_OK;
+}
+
+int sva_frame_set_params(sva_ctx* c, const sva_params* p) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+    SVA_TRY(check_params(c, p));
+    if (p->width != c->prm.width || p->height != c->prm.height) return c->fail(SVA_ERR_BAD_ARG, "set_params cannot change the image size");
+    c->prm = *p;
+    c->pair_begin = 0; c->pair_end = p->n_pairs;
+    c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;  // volumes of the old disparity range are not valid for the new one
+    return SVA_OK;
+}
+
+int sva_frame_sgm_directions(sva_ctx* c, const void* cost_dev, int32_t slice_disp, uint32_t dir_mask, int32_t rows_alloc, void** out_s_ptr, size_t* out_bytes) {
+    if (!c || !cost_dev) return SVA_ERR_BAD_ARG;
+    if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(sva_run_sgm_dirs(c, (const uint16_t*)cost_dev, slice_disp, dir_mask, rows_alloc));
+    const int rows = rows_alloc > c->prm.height ? rows_alloc : c->prm.height;
+    if (out_s_ptr) *out_s_ptr = c->S.p;
+    if (out_bytes) *out_bytes = (size_t)c->prm.width * rows * c->prm.num_disp * 2;
+    return SVA_OK;
+}
+
+int sva_frame_wta_rows(sva_ctx* c, const void* s_rows_dev, int32_t y0, int32_t rows) {
+    if (!c || !s_rows_dev) return SVA_ERR_BAD_ARG;
+    if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(sva_run_wta_rows(c, (const uint16_t*)s_rows_dev, y0, rows));
+    c->have_disp = true;
+    return SVA_OK;
+}
+
+int sva_frame_download_disparity_rows(sva_ctx* c, int32_t rows, uint16_t* out_disp, float* out_sub) {
+    if (!c || !out_disp || rows < 1 || rows > c->prm.height) return SVA_ERR_BAD_ARG;
+    if (!c->have_disp) return c->fail(SVA_ERR_STATE, "disparity not computed");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    const size_t px = (size_t)c->prm.width * rows;
+    SVA_CUDA_OK(c, cudaMemcpyAsync(out_disp, c->disp.p, px * 2, cudaMemcpyDeviceToHost, c->stream));
+    if (out_sub) SVA_CUDA_OK(c, cudaMemcpyAsync(out_sub, c->subpix.p, px * 4, cudaMemcpyDeviceToHost, c->stream));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SVA_OK;
 }
 
 /* ---- streaming form of sva_depth_from_array: a capture stream, two frames in flight ---------------------------------------------

@@ -77,6 +77,106 @@ def pair_sharded_depth(ctx, p, ref, others, mask, rank, world, owner=0, group=No
     return ctx.download_disparity()
 
 
+def direction_masks(n_paths, world):
+    """path directions dealt round-robin: rank r aggregates directions r, r + world, ... (bit i = direction i of the C ABI's order)"""
+    return [sum(1 << d for d in range(r, n_paths, world)) for r in range(world)]
+
+
+def row_blocks(height, world):
+    """equal row blocks for the reduce-scatter of the partial aggregation volumes: (rows per block, [(y0, y1)] per rank); the last blocks
+    may be short or empty, the volume is padded to rows_per * world rows"""
+    rows_per = -(-height // world)
+    return rows_per, [(min(height, r * rows_per), min(height, (r + 1) * rows_per)) for r in range(world)]
+
+
+def slice_params(p, rank, world):
+    """rank's disparity slice of p: D / world disparities starting at min_disp + rank * D / world (same pairs, shift, cap, penalties)"""
+    if p.num_disp % world or (p.num_disp // world) % 8:
+        raise ValueError("num_disp must split into %d slices of a multiple of 8 disparities" % world)
+    ps = type(p).from_buffer_copy(p)
+    ps.num_disp = p.num_disp // world
+    ps.min_disp = p.min_disp + rank * ps.num_disp
+    return ps
+
+
+def slice_sharded_compute(ctx, p, rank, world, group=None, keep=None):
+    """Device part of slice_sharded_depth for a frame that is already uploaded on every rank (with any disparity range of the same
+    images): steps 1-5 below; afterwards the rank's rows of the maps are in the library (ctx.download_disparity_rows).  Returns (y0, y1)."""
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    keep = keep if keep is not None else {}
+    ds = p.num_disp // world
+    ctx.set_params(slice_params(p, rank, world))
+    ctx.run(abi.STAGE_AD)
+    ctx.run(abi.STAGE_BOX)
+    cptr, cbytes = ctx.cost_device_ptr()
+    cslice = torch.as_tensor(_CudaAlias(cptr, cbytes // 4), device="cuda")
+    if keep.get("call") is None or keep["call"].numel() != world * cslice.numel():
+        keep["call"] = torch.empty(world * cslice.numel(), dtype=torch.int32, device="cuda")
+    call = keep["call"]
+    if world > 1:
+        dist.all_gather_into_tensor(call, cslice, group=group)
+    else:
+        call.copy_(cslice)
+    ctx.set_params(p)
+    rows_per, blocks = row_blocks(p.height, world)
+    bits = direction_masks(p.n_paths, world)[rank]
+    words_row = p.width * p.num_disp // 2
+    if bits:
+        sptr, sbytes = ctx.sgm_directions(call.data_ptr(), ds, bits, rows_per * world)
+        spart = torch.as_tensor(_CudaAlias(sptr, sbytes // 4), device="cuda")
+    else:  # more ranks than directions: nothing to add
+        if keep.get("zero") is None or keep["zero"].numel() != rows_per * world * words_row:
+            keep["zero"] = torch.zeros(rows_per * world * words_row, dtype=torch.int32, device="cuda")
+        spart = keep["zero"]
+    if keep.get("srows") is None or keep["srows"].numel() != rows_per * words_row:
+        keep["srows"] = torch.empty(rows_per * words_row, dtype=torch.int32, device="cuda")
+    srows = keep["srows"]
+    if world > 1:
+        dist.reduce_scatter_tensor(srows, spart, op=dist.ReduceOp.SUM, group=group)
+    else:
+        srows.copy_(spart[:srows.numel()])
+    y0, y1 = blocks[rank]
+    if y1 > y0:
+        ctx.wta_rows(srows.data_ptr(), y0, y1 - y0)
+    return y0, y1
+
+
+def slice_sharded_depth(ctx, p, ref, others, mask, rank, world, group=None, keep=None):
+    """One frame sharded WITHOUT a volume reduction (the alternative to pair_sharded_depth for configuration c3):
+      1. rank r computes its DISPARITY SLICE of the cost volume from all pairs (K1a + K1b, no exchange);
+      2. all-gather of the slices (slice-major volume on every rank);
+      3. rank r aggregates its share of the SGM DIRECTIONS over the whole volume;
+      4. reduce-scatter of the partial sums by ROW BLOCKS (packed int32: 8 paths x 8190 <= 65520, carry-free, bit-exact in any order);
+      5. rank r runs WTA / left-right check / sub-pixel on its rows; the maps are gathered on rank 0.
+    Every rank holds the frame's images.  ctx must run on torch's current stream.  Returns (disp, subpix) on rank 0, None elsewhere.
+    `keep` (a dict) caches the gather / scatter buffers across frames."""
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    ctx.upload(slice_params(p, rank, world), ref, others, mask)
+    y0, y1 = slice_sharded_compute(ctx, p, rank, world, group, keep)
+    rows_per = row_blocks(p.height, world)[0]
+    d_t = torch.full((rows_per, p.width), abi.SVA_DISP_INVALID, dtype=torch.int32)
+    s_t = torch.full((rows_per, p.width), -1.0, dtype=torch.float32)
+    if y1 > y0:
+        d, s = ctx.download_disparity_rows(y1 - y0)
+        d_t[:y1 - y0] = torch.from_numpy(d.astype(np.int32))
+        s_t[:y1 - y0] = torch.from_numpy(s)
+    if world == 1:
+        return d_t[:p.height].numpy().astype(np.uint16), s_t[:p.height].numpy()
+    d_all = [torch.empty_like(d_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    s_all = [torch.empty_like(s_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    dist.gather(d_t.cuda(), d_all, dst=0, group=group)
+    dist.gather(s_t.cuda(), s_all, dst=0, group=group)
+    if rank != 0:
+        return None
+    disp = torch.cat(d_all)[:p.height].cpu().numpy().astype(np.uint16)
+    sub = torch.cat(s_all)[:p.height].cpu().numpy()
+    return disp, sub
+
+
 def numpy_pack(a_u16):
     """[H][W][D] u16 (D even) -> int32 view, the layout the GPU path reduces"""
     return np.ascontiguousarray(a_u16).view(np.int32)

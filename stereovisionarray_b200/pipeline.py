@@ -136,6 +136,32 @@ class DepthContext:
     def mark_ad_ready(self):
         check(self._h, self._L.sva_frame_mark_ad_ready(self._h))
 
+    # ---- multi-GPU building blocks: disparity-slice / direction / row sharding of one frame (dist.slice_sharded_depth) ----
+    def cost_device_ptr(self):
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check(self._h, self._L.sva_frame_cost_device_ptr(self._h, C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def set_params(self, p):
+        check(self._h, self._L.sva_frame_set_params(self._h, C.byref(p)))
+        self.params = p
+
+    def sgm_directions(self, cost_ptr, slice_disp, dir_mask, rows_alloc=0):
+        """aggregate the directions of dir_mask on a device cost volume (slice-major when slice_disp > 0) -> (device ptr, bytes) of the partial S"""
+        ptr, n = C.c_void_p(), C.c_size_t()
+        check(self._h, self._L.sva_frame_sgm_directions(self._h, C.c_void_p(cost_ptr), int(slice_disp), C.c_uint32(dir_mask), int(rows_alloc), C.byref(ptr), C.byref(n)))
+        return ptr.value, n.value
+
+    def wta_rows(self, s_rows_ptr, y0, rows):
+        check(self._h, self._L.sva_frame_wta_rows(self._h, C.c_void_p(s_rows_ptr), int(y0), int(rows)))
+
+    def download_disparity_rows(self, rows):
+        p = self.params
+        disp = np.empty((rows, p.width), np.uint16)
+        sub = np.empty((rows, p.width), np.float32)
+        check(self._h, self._L.sva_frame_download_disparity_rows(self._h, int(rows), _p(disp, C.c_uint16), _p(sub, C.c_float)))
+        return disp, sub
+
     # ---- one call, host in / host out (the e2e path) ----
     def depth_from_array(self, p, ref, others, mask=None, disp=None, sub=None):
         r, rk = abi.image_u8(ref)

@@ -89,3 +89,25 @@ def test_pair_sharded_reduce_and_frame_partition(world):
     assert ok_reduce, "packed int32 reduce of the AD partials != full AD volume"
     assert ok_pipe, "pipeline from the reduced volume != single-process pipeline"
     assert ok_frames, "frame-partitioned results != serial results"
+
+
+def test_slice_direction_row_plans():
+    """host-side plans of dist.slice_sharded_depth (pure Python; the device path is covered by tests/test_gpu_volume.py and, over real
+    GPUs, by tools/check_slice_sharded.py under torchrun)"""
+    from stereovisionarray_b200 import abi, dist as sdist
+    for world in (1, 2, 4, 8):
+        masks = sdist.direction_masks(8, world)
+        assert len(masks) == world and sum(masks) == 0xFF and all(a & b == 0 for i, a in enumerate(masks) for b in masks[i + 1:])
+    assert sdist.direction_masks(4, 8) == [1, 2, 4, 8, 0, 0, 0, 0]
+    rows_per, blocks = sdist.row_blocks(2160, 8)
+    assert rows_per == 270 and blocks[0] == (0, 270) and blocks[-1] == (1890, 2160)
+    rows_per, blocks = sdist.row_blocks(70, 4)
+    assert rows_per == 18 and blocks == [(0, 18), (18, 36), (36, 54), (54, 70)]
+    assert sdist.row_blocks(10, 8)[1][-1] == (10, 10)  # empty trailing blocks
+    p = abi.make_params(64, 48, 256, [(-1, 0), (1, 1)], win_half=4, min_disp=3)
+    ps = sdist.slice_params(p, 5, 8)
+    assert (ps.num_disp, ps.min_disp, ps.n_pairs, ps.cost_shift, ps.p2) == (32, 3 + 5 * 32, 2, p.cost_shift, p.p2)
+    assert (p.num_disp, p.min_disp) == (256, 3)  # the original is untouched
+    import pytest
+    with pytest.raises(ValueError):
+        sdist.slice_params(p, 0, 3)

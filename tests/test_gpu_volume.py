@@ -99,6 +99,58 @@ def test_stream_of_frames_matches_the_one_call_path(ctx, oracle):
     assert np.array_equal(d1, outs[0][0]) and np.array_equal(s1, outs[0][1])
 
 
+@pytest.mark.parametrize("D,G", [(64, 4), (96, 2), (128, 8)])
+def test_slice_direction_row_sharding_emulated_on_one_gpu(ctx, oracle, D, G):
+    """dist.slice_sharded_depth's building blocks, with the collectives replaced by local concatenation / addition: 4 disparity slices ->
+    slice-major cost volume -> direction shares summed -> row blocks through K3 == the oracle's whole pipeline, bit for bit"""
+    import torch
+    from stereovisionarray_b200 import dist as sdist
+    h, w = 70, 150
+    sc = synth.make_scene(h, w, D, OFF8, 41, min_disp=2, face=True)
+    p = abi.make_params(w, h, D, OFF8, win_half=5, n_paths=8, lr_gx=-1, min_disp=2)
+    alias = lambda ptr, nbytes: torch.as_tensor(sdist._CudaAlias(ptr, nbytes // 4), device="cuda")
+    slices = []
+    for r in range(G):
+        ctx.upload(sdist.slice_params(p, r, G), sc["ref"], sc["others"], sc["mask"])
+        ctx.run(abi.STAGE_AD)
+        ctx.run(abi.STAGE_BOX)
+        ctx.synchronize()
+        slices.append(alias(*ctx.cost_device_ptr()).clone())
+    call = torch.cat(slices)
+    torch.cuda.synchronize()
+    ctx.set_params(p)
+    rows_per, blocks = sdist.row_blocks(h, G)
+    total = None
+    for r in range(G):
+        sptr, sbytes = ctx.sgm_directions(call.data_ptr(), D // G, sdist.direction_masks(8, G)[r], rows_per * G)
+        ctx.synchronize()
+        part = alias(sptr, sbytes).clone()
+        total = part if total is None else total + part
+    torch.cuda.synchronize()
+    C_o = oracle.box_cost(p, oracle.ad_volume(p, sc["ref"], sc["others"]))
+    S_o = oracle.sgm_aggregate(p, C_o)
+    S_g = total.cpu().numpy().view(np.uint16).reshape(rows_per * G, w, D)
+    assert np.array_equal(S_g[:h], S_o) and not S_g[h:].any()
+    disp = np.empty((h, w), np.uint16)
+    sub = np.empty((h, w), np.float32)
+    words_row = w * D // 2
+    for y0, y1 in blocks:
+        if y1 > y0:
+            rows = total[y0 * words_row:y1 * words_row].clone()
+            torch.cuda.synchronize()
+            ctx.wta_rows(rows.data_ptr(), y0, y1 - y0)
+            disp[y0:y1], sub[y0:y1] = ctx.download_disparity_rows(y1 - y0)
+    disp_o, sub_o = oracle.wta(p, S_o, sc["mask"])
+    assert np.array_equal(disp, disp_o) and np.array_equal(sub, sub_o)
+    # and the world-size-1 path of the real function (it needs the library on torch's stream)
+    ctx.set_stream(torch.cuda.current_stream().cuda_stream)
+    try:
+        d1, s1 = sdist.slice_sharded_depth(ctx, p, sc["ref"], sc["others"], sc["mask"], 0, 1)
+    finally:
+        ctx.use_own_stream()
+    assert np.array_equal(d1, disp_o) and np.array_equal(s1, sub_o)
+
+
 def test_pair_range_partials_sum_to_full(ctx, oracle):
     """what the pair-sharded multi-GPU reduce relies on: AD partials over disjoint pair ranges add up exactly"""
     h, w, D = 48, 64, 32
