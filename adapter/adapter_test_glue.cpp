@@ -44,3 +44,25 @@ extern "C" int adapter_driver(const uint8_t* const* images25, int w, int h, cons
         return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
+
+// the consumers of the depth output under their reference names (functions.h:24,28,30,32): warp a depth map, lift it to a cloud, re-project it
+extern "C" long long adapter_depth_consumers(const double* depth, int w, int h, int cam_in, int cam_out, double* out_shifted, double* out_cloud,
+                                             double* out_map, int* out_group_sizes) {
+    try {
+        double f = 0.05, sensor_size = 0.036, pixelSize = sensor_size / w;
+        std::vector<Camera> cameras;
+        for (int y = 0; y < 5; y++)
+            for (int x = 0; x < 5; x++) cameras.push_back(Camera(f, cv::Point3d{-0.1 + x * 0.05, -0.1 + y * 0.05, -0.75}, pixelSize));
+        cv::Mat d(h, w, CV_64FC1);
+        std::memcpy(d.data, depth, sizeof(double) * (size_t)w * h);
+        cv::Mat shifted = shiftPerspective2(cameras[cam_in], cameras[cam_out], d);
+        std::memcpy(out_shifted, shifted.data, sizeof(double) * (size_t)w * h);
+        std::vector<cv::Point3d> cloud = DepthMapToPoints3D(d, cameras[cam_in], cv::Size{w, h});
+        for (size_t i = 0; i < cloud.size(); i++) { out_cloud[3 * i] = cloud[i].x; out_cloud[3 * i + 1] = cloud[i].y; out_cloud[3 * i + 2] = cloud[i].z; }
+        cv::Mat map = Points3DToDepthMap(cloud, cameras[cam_out], cv::Size{w, h});
+        std::memcpy(out_map, map.data, sizeof(double) * (size_t)w * h);
+        auto groups = getGroups(cameras, "CHESS");
+        for (size_t g = 0; g < groups.size() && g < 16; g++) out_group_sizes[g] = (int)groups[g].size();
+        return (long long)cloud.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}

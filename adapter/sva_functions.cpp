@@ -126,3 +126,43 @@ cv::Mat svaMatchLiteral(std::vector<cv::Mat>& images, std::vector<Camera>& camer
     check(sva_match_literal(ctx(), imgs.data(), cams.data(), (int)imgs.size(), pr.data(), (int)pairs.size(), &m, kernelSize, rayNear, rayFar, out.data), "svaMatchLiteral");
     return out;
 }
+
+// ---- consumers of the depth output (functions.h:24,28,30,32) ----
+cv::Mat shiftPerspective2(Camera inputCam, Camera outputCam, cv::Mat& depthMap) {  // src/functions.cpp:79-104; depthMap is CV_64FC1, continuous rows
+    cv::Mat src = depthMap.clone();  // clone() is continuous, whatever view the caller passed
+    cv::Mat out(src.size(), src.type());
+    sva_camera ci = cam(inputCam), co = cam(outputCam);
+    check(sva_shift_perspective2(ctx(), &ci, &co, (const double*)src.data, src.rows, src.cols, (double*)out.data), "shiftPerspective2");
+    return out;
+}
+cv::Mat Points3DToDepthMap(std::vector<cv::Point3d>& points, Camera camera, cv::Size resolution) {  // src/functions.cpp:118-133
+    cv::Mat out(resolution, CV_64FC1);
+    sva_camera c = cam(camera);
+    static_assert(sizeof(cv::Point3d) == 3 * sizeof(double), "Point3d must be three packed doubles");
+    check(sva_points3d_to_depth_map(ctx(), points.empty() ? nullptr : &points[0].x, (int64_t)points.size(), &c, resolution.width, resolution.height,
+                                    (double*)out.data), "Points3DToDepthMap");
+    return out;
+}
+std::vector<cv::Point3d> DepthMapToPoints3D(cv::Mat& depthMap, Camera camera, cv::Size resolution) {  // src/functions.cpp:135-146
+    cv::Mat src = depthMap.clone();  // clone() is continuous, whatever view the caller passed
+    std::vector<cv::Point3d> pts((size_t)src.rows * src.cols);
+    sva_camera c = cam(camera);
+    int64_t n = 0;
+    check(sva_depth_map_to_points3d(ctx(), (const double*)src.data, src.rows, src.cols, &c, resolution.width, resolution.height,
+                                    pts.empty() ? nullptr : &pts[0].x, (int64_t)pts.size(), &n), "DepthMapToPoints3D");
+    pts.resize((size_t)n);
+    return pts;
+}
+std::vector<std::vector<std::array<int, 2>>> getGroups(std::vector<Camera>& cameras, std::string groupType) {  // src/functions.cpp:107-116
+    std::vector<int32_t> pairs(2 * 256), sizes(64);
+    int ng = sva_get_groups((int32_t)cameras.size(), groupType.c_str(), pairs.data(), 256, sizes.data(), 64);
+    if (ng < 0) throw cv::Exception("getGroups: bad argument");
+    std::vector<std::vector<std::array<int, 2>>> groups;
+    size_t o = 0;
+    for (int g = 0; g < ng; g++) {
+        std::vector<std::array<int, 2>> grp;
+        for (int j = 0; j < sizes[g]; j++, o++) grp.push_back({pairs[2 * o], pairs[2 * o + 1]});
+        groups.push_back(grp);
+    }
+    return groups;
+}

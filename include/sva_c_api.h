@@ -124,6 +124,21 @@ int sva_improve_with_disparity(sva_ctx* ctx, const sva_image_u8* disparity, cons
 /* depth = baseline * f / (disparity * pixel_size) in f64 — src/CameraStereoVision.cpp:47,98-100 (inf where disparity == 0). */
 int sva_disparity_to_depth(sva_ctx* ctx, const sva_image_u8* disparity, double baseline, double f, double pixel_size, double* out_depth);
 
+/* ---- consumers of the depth output, f64, bit-exact with the reference's serial loops ---------------------------- */
+/* shiftPerspective2 — include/functions.h:24, src/functions.cpp:79-104: forward-warp a depth map into another camera's view; where several
+ * sources land on a pixel the one the reference visits last (x outer, y inner) wins; pixels nothing lands on are 0 (uninitialised there). */
+int sva_shift_perspective2(sva_ctx* ctx, const sva_camera* input_cam, const sva_camera* output_cam, const double* depth, int32_t rows, int32_t cols,
+                           double* out);
+/* Points3DToDepthMap — include/functions.h:30, src/functions.cpp:118-133: depth = p.z - camera.z at project(p) + resolution/2; the last
+ * point in list order wins; unwritten pixels are 0. */
+int sva_points3d_to_depth_map(sva_ctx* ctx, const double* points_xyz, int64_t n_points, const sva_camera* cam, int32_t width, int32_t height, double* out);
+/* DepthMapToPoints3D — include/functions.h:32, src/functions.cpp:135-146: one point per pixel with depth > 0.1, in column-major pixel order.
+ * *out_count = number of points; at most `cap` are written. */
+int sva_depth_map_to_points3d(sva_ctx* ctx, const double* depth, int32_t rows, int32_t cols, const sva_camera* cam, int32_t width, int32_t height,
+                              double* out_xyz, int64_t cap, int64_t* out_count);
+/* getGroups — include/functions.h:28, src/functions.cpp:107-116.  Returns the number of groups. */
+int sva_get_groups(int32_t n_cameras, const char* group_type, int32_t* out_pairs, int32_t cap_pairs, int32_t* out_sizes, int32_t cap_groups);
+
 /* The whole volume-mode pipeline (cost volume -> SGM -> WTA/LR/sub-pixel), DESIGN.md §3.
  * others[n_pairs] are the other views in pair order.  out_disp: u16 (min_disp + d, SVA_DISP_INVALID when rejected);
  * out_subpix (may be NULL): f32. */

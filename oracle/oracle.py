@@ -104,6 +104,36 @@ class Oracle:
         self.lib.orc_disparity_to_depth(C.byref(d), C.c_double(baseline), C.c_double(f), C.c_double(pixel_size), _ptr(out, C.c_double))
         return out
 
+    # ---- consumers of the depth output ----
+    def shift_perspective2(self, in_cam, out_cam, depth):
+        d = np.ascontiguousarray(depth, dtype=np.float64)
+        out = np.zeros_like(d)
+        self.lib.orc_shift_perspective2(C.byref(in_cam), C.byref(out_cam), _ptr(d, C.c_double), d.shape[0], d.shape[1], _ptr(out, C.c_double))
+        return out
+
+    def points3d_to_depth_map(self, points, cam, width, height):
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((height, width), dtype=np.float64)
+        self.lib.orc_points3d_to_depth_map(_ptr(pts, C.c_double), C.c_longlong(len(pts)), C.byref(cam), width, height, _ptr(out, C.c_double))
+        return out
+
+    def depth_map_to_points3d(self, depth, cam, width, height):
+        d = np.ascontiguousarray(depth, dtype=np.float64)
+        out = np.zeros((d.size, 3), dtype=np.float64)
+        self.lib.orc_depth_map_to_points3d.restype = C.c_longlong
+        n = self.lib.orc_depth_map_to_points3d(_ptr(d, C.c_double), d.shape[0], d.shape[1], C.byref(cam), width, height, _ptr(out, C.c_double), C.c_longlong(d.size))
+        return out[:n].copy()
+
+    def get_groups(self, n_cameras, group_type="CHESS"):
+        pairs = np.zeros((256, 2), dtype=np.int32)
+        sizes = np.zeros(64, dtype=np.int32)
+        ng = self.lib.orc_get_groups(n_cameras, group_type.encode(), _ptr(pairs, C.c_int32), 256, _ptr(sizes, C.c_int32), 64)
+        out, o = [], 0
+        for g in range(ng):
+            out.append(pairs[o:o + sizes[g]].copy())
+            o += sizes[g]
+        return out
+
     # ---- volume ----
     def _shape(self, p):
         return (p.height, p.width, p.num_disp)
@@ -208,6 +238,38 @@ class Reference:
         out = np.zeros((cap, 2), dtype=np.int32)
         n = self.lib.ref_bresenham(a[0], a[1], b[0], b[1], _ptr(out, C.c_int32), cap)
         return out[:n].copy()
+
+    def shift_perspective2(self, in_cam, out_cam, depth):
+        d = np.ascontiguousarray(depth, dtype=np.float64)
+        out = np.zeros_like(d)
+        rc = self.lib.ref_shift_perspective2(_ptr(_cam5(in_cam), C.c_double), _ptr(_cam5(out_cam), C.c_double), _ptr(d, C.c_double), d.shape[1], d.shape[0], _ptr(out, C.c_double))
+        assert rc == 0, self.lib.ref_last_error()
+        return out
+
+    def points3d_to_depth_map(self, points, cam, width, height):
+        pts = np.ascontiguousarray(points, dtype=np.float64).reshape(-1, 3)
+        out = np.zeros((height, width), dtype=np.float64)
+        rc = self.lib.ref_points3d_to_depth_map(_ptr(pts, C.c_double), C.c_longlong(len(pts)), _ptr(_cam5(cam), C.c_double), width, height, _ptr(out, C.c_double))
+        assert rc == 0, self.lib.ref_last_error()
+        return out
+
+    def depth_map_to_points3d(self, depth, cam, width, height):
+        d = np.ascontiguousarray(depth, dtype=np.float64)
+        out = np.zeros((d.size, 3), dtype=np.float64)
+        self.lib.ref_depth_map_to_points3d.restype = C.c_longlong
+        n = self.lib.ref_depth_map_to_points3d(_ptr(d, C.c_double), d.shape[1], d.shape[0], _ptr(_cam5(cam), C.c_double), width, height, _ptr(out, C.c_double), C.c_longlong(d.size))
+        assert n >= 0, self.lib.ref_last_error()
+        return out[:n].copy()
+
+    def get_groups(self, n_cameras, group_type="CHESS"):
+        pairs = np.zeros((256, 2), dtype=np.int32)
+        sizes = np.zeros(64, dtype=np.int32)
+        ng = self.lib.ref_get_groups(n_cameras, group_type.encode(), _ptr(pairs, C.c_int32), 256, _ptr(sizes, C.c_int32), 64)
+        out, o = [], 0
+        for g in range(ng):
+            out.append(pairs[o:o + sizes[g]].copy())
+            o += sizes[g]
+        return out
 
     def get_camera_pairs(self, n_cameras, pair_type, camera_num=-1):
         out = np.zeros((64, 2), dtype=np.int32)

@@ -11,10 +11,12 @@
 //    is an INPUT predicate to the depth path (src/CameraStereoVision.cpp:21,53).
 //  * main() of src/CameraStereoVision.cpp is renamed at compile time (-Dmain=sva_ref_main) so
 //    the inline hot loop nest (:49-95) can be executed on harness-supplied images.
+#include <fcntl.h>
 #include <unistd.h>
 
 #include <cstdint>
 #include <cstring>
+#include <iostream>
 #include <string>
 
 #include "Camera.h"
@@ -116,6 +118,58 @@ int ref_improve_with_disparity(const uint8_t* disparity, const uint8_t* center, 
         cv::Mat r = improveWithDisparity(d, c, imgs, cams, window_size);
         copy_out_u8(r, out);
         return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// ---- consumers of the depth output ----
+static cv::Mat wrap_f64(const double* data, int w, int h) {
+    cv::Mat m(h, w, CV_64FC1);
+    for (int y = 0; y < h; y++) std::memcpy(m.data + (size_t)y * m.step, data + (size_t)y * w, sizeof(double) * w);
+    return m;
+}
+// shiftPerspective2 — src/functions.cpp:79-104.  The reference leaves unwritten pixels uninitialised; `written` marks the pixels it stores.
+int ref_shift_perspective2(const double* in_cam5, const double* out_cam5, const double* depth, int w, int h, double* out) {
+    try {
+        cv::Mat d = wrap_f64(depth, w, h);
+        cv::Mat r = shiftPerspective2(make_cam(in_cam5), make_cam(out_cam5), d);
+        for (int y = 0; y < h; y++) std::memcpy(out + (size_t)y * w, r.data + (size_t)y * r.step, sizeof(double) * w);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// Points3DToDepthMap — src/functions.cpp:118-133
+int ref_points3d_to_depth_map(const double* xyz, long long n, const double* cam5, int w, int h, double* out) {
+    try {
+        std::vector<cv::Point3d> pts;
+        for (long long i = 0; i < n; i++) pts.push_back(cv::Point3d{xyz[3 * i], xyz[3 * i + 1], xyz[3 * i + 2]});
+        int saved = dup(1), devnull = open("/dev/null", O_WRONLY);  // the function prints the size to std::cout
+        fflush(stdout); dup2(devnull, 1);
+        cv::Mat r = Points3DToDepthMap(pts, make_cam(cam5), cv::Size{w, h});
+        std::cout.flush(); dup2(saved, 1); close(devnull); close(saved);
+        for (int y = 0; y < h; y++) std::memcpy(out + (size_t)y * w, r.data + (size_t)y * r.step, sizeof(double) * w);
+        return 0;
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// DepthMapToPoints3D — src/functions.cpp:135-146; returns the number of points (only `cap` are written)
+long long ref_depth_map_to_points3d(const double* depth, int w, int h, const double* cam5, int res_w, int res_h, double* out_xyz, long long cap) {
+    try {
+        cv::Mat d = wrap_f64(depth, w, h);
+        std::vector<cv::Point3d> pts = DepthMapToPoints3D(d, make_cam(cam5), cv::Size{res_w, res_h});
+        for (long long i = 0; i < (long long)pts.size() && i < cap; i++) { out_xyz[3 * i] = pts[i].x; out_xyz[3 * i + 1] = pts[i].y; out_xyz[3 * i + 2] = pts[i].z; }
+        return (long long)pts.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+// getGroups — src/functions.cpp:107-116; pairs flattened, sizes[g] = pairs in group g; returns the number of groups
+int ref_get_groups(int n_cameras, const char* group_type, int* out_pairs, int cap_pairs, int* out_sizes, int cap_groups) {
+    try {
+        std::vector<Camera> cams;
+        for (int i = 0; i < n_cameras; i++) cams.push_back(Camera(0.05, cv::Point3d{0, 0, 0}, 1e-4));
+        auto groups = getGroups(cams, std::string(group_type));
+        int np = 0;
+        for (size_t g = 0; g < groups.size(); g++) {
+            if ((int)g < cap_groups) out_sizes[g] = (int)groups[g].size();
+            for (auto& pr : groups[g]) { if (np < cap_pairs) { out_pairs[2 * np] = pr[0]; out_pairs[2 * np + 1] = pr[1]; } np++; }
+        }
+        return (int)groups.size();
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }
 

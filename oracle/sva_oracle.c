@@ -215,6 +215,70 @@ int orc_disparity_to_depth(const sva_image_u8* disp, double baseline, double f, 
     return SVA_OK;
 }
 
+/* ---- consumers of the depth output: pinned against the reference's code by tests/test_oracle_vs_reference.py ---- */
+
+/* shiftPerspective2 — src/functions.cpp:79-104.  x outer, y inner, later sources overwrite earlier ones; unwritten pixels are 0 here
+ * (uninitialised in the reference). */
+int orc_shift_perspective2(const sva_camera* in_cam, const sva_camera* out_cam, const double* depth, int rows, int cols, double* out) {
+    double pmx = (in_cam->pos[0] - out_cam->pos[0]) * in_cam->f / in_cam->pixel_size;   /* :82 */
+    double pmy = (in_cam->pos[1] - out_cam->pos[1]) * in_cam->f / in_cam->pixel_size;   /* :83 */
+    memset(out, 0, sizeof(double) * (size_t)rows * cols);
+    for (int x = 0; x < cols; x++)                                                        /* :86 */
+        for (int y = 0; y < rows; y++) {                                                  /* :87 */
+            double d = depth[(size_t)y * cols + x];
+            if (d < 0.5) continue;                                                        /* :89 */
+            int sx = (int)(pmx / d) + x, sy = (int)(pmy / d) + y;                         /* :91-92 */
+            if (sy >= rows || sy < 0 || sx >= cols || sx < 0) continue;                   /* :93 */
+            out[(size_t)sy * cols + sx] = d;                                              /* :95 */
+        }
+    return SVA_OK;
+}
+
+/* Points3DToDepthMap — src/functions.cpp:118-133.  halfRes = resolution / 2 (integer); later points overwrite earlier ones. */
+int orc_points3d_to_depth_map(const double* xyz, long long n, const sva_camera* cam, int width, int height, double* out) {
+    int hx = width / 2, hy = height / 2;                                                  /* :122 */
+    memset(out, 0, sizeof(double) * (size_t)width * height);
+    for (long long i = 0; i < n; i++) {
+        int32_t px[2];
+        orc_camera_project(cam, xyz + 3 * i, px);                                         /* :125 */
+        int x = px[0] + hx, y = px[1] + hy;
+        if (x >= 0 && x < width && y >= 0 && y < height) out[(size_t)y * width + x] = xyz[3 * i + 2] - cam->pos[2];   /* :126-128 */
+    }
+    return SVA_OK;
+}
+
+/* DepthMapToPoints3D — src/functions.cpp:135-146.  u (column) outer, v (row) inner; returns the point count, writes at most cap. */
+long long orc_depth_map_to_points3d(const double* depth, int rows, int cols, const sva_camera* cam, int width, int height, double* out_xyz, long long cap) {
+    int hx = width / 2, hy = height / 2;                                                  /* :137 */
+    long long n = 0;
+    for (int u = 0; u < cols; u++)                                                        /* :139 */
+        for (int v = 0; v < rows; v++) {                                                  /* :140 */
+            double d = depth[(size_t)v * cols + u];
+            if (d > 0.1) {                                                                /* :142 */
+                int32_t px[2] = {u - hx, v - hy};
+                double r[3];
+                orc_camera_inv_project(cam, px, r);
+                if (n < cap) { out_xyz[3 * n] = cam->pos[0] + r[0] * d; out_xyz[3 * n + 1] = cam->pos[1] + r[1] * d; out_xyz[3 * n + 2] = cam->pos[2] + r[2] * d; }  /* :143 */
+                n++;
+            }
+        }
+    return n;
+}
+
+/* getGroups — src/functions.cpp:107-116: "CHESS" = the CROSS pairs of every second camera 0, 2, ..., 24 */
+int orc_get_groups(int32_t n_cameras, const char* group_type, int32_t* out_pairs, int32_t cap_pairs, int32_t* out_sizes, int32_t cap_groups) {
+    int ng = 0, np = 0;
+    if (strcmp(group_type, "CHESS") == 0)
+        for (int i = 0; i < 25; i += 2) {                                                 /* :111 */
+            int32_t tmp[128];
+            int n = orc_get_camera_pairs(n_cameras, SVA_CROSS, i, tmp, 64);               /* :112 */
+            if (ng < cap_groups) out_sizes[ng] = n;
+            for (int j = 0; j < n; j++) { if (np < cap_pairs) { out_pairs[2 * np] = tmp[2 * j]; out_pairs[2 * np + 1] = tmp[2 * j + 1]; } np++; }
+            ng++;
+        }
+    return ng;
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Volume mode (frozen spec) — no reference counterpart: parity UNPINNED by the reference.
  * ---------------------------------------------------------------------------------------------- */

@@ -16,25 +16,11 @@
 #include <climits>
 
 #include "sva_common.cuh"
+#include "sva_cam.cuh"
 
 int sva_launch_box(sva_ctx* ctx, const uint16_t* A, void* out, int W, int H, int D, int k, const sva_params* prm, bool raw, bool apply_validity);
 
 #define LIT_CHUNK 64
-
-struct DevCam { double px, py, pz, f, ps; };
-
-// Camera::inv_project — src/Camera.cpp:25-33
-__device__ __forceinline__ void dev_inv_project(const DevCam& c, int u, int v, double& rx, double& ry, double& rz) {
-    double vx = __dmul_rn((double)u, c.ps), vy = __dmul_rn((double)v, c.ps), vz = c.f;
-    double n = __dsqrt_rn(__dadd_rn(__dadd_rn(__dmul_rn(vx, vx), __dmul_rn(vy, vy)), __dmul_rn(vz, vz)));
-    rx = __ddiv_rn(vx, n); ry = __ddiv_rn(vy, n); rz = __ddiv_rn(vz, n);
-}
-// Camera::project — src/Camera.cpp:15-22
-__device__ __forceinline__ void dev_project(const DevCam& c, double X, double Y, double Z, int& u, int& v) {
-    double mult = __ddiv_rn(__ddiv_rn(c.f, __dsub_rn(Z, c.pz)), c.ps);
-    u = (int)__dmul_rn(__dsub_rn(X, c.px), mult);
-    v = (int)__dmul_rn(__dsub_rn(Y, c.py), mult);
-}
 
 // incremental form of plotLineLow / plotLineHigh — src/functions.cpp:253-321 (first argument = the definition's point2)
 struct Bres {

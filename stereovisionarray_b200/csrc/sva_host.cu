@@ -107,4 +107,25 @@ int sva_grid_pairs(int32_t grid_rows, int32_t grid_cols, int32_t ref_index, int3
     return n;
 }
 
+/* getGroups — include/functions.h:28, src/functions.cpp:107-116: "CHESS" = the CROSS pairs of cameras 0, 2, ..., 24 (13 reference views of
+ * the 5x5 array); any other name yields no groups, as in the reference.  Pairs are flattened, out_sizes[g] = pairs of group g. */
+int sva_get_groups(int32_t n_cameras, const char* group_type, int32_t* out_pairs, int32_t cap_pairs, int32_t* out_sizes, int32_t cap_groups) {
+    if (!group_type || cap_pairs < 0 || cap_groups < 0 || (cap_pairs > 0 && !out_pairs) || (cap_groups > 0 && !out_sizes)) return SVA_ERR_BAD_ARG;
+    int ng = 0, np = 0;
+    if (std::string(group_type) == "CHESS") {
+        for (int i = 0; i < 25; i += 2) {
+            int32_t tmp[128];
+            const int n = sva_get_camera_pairs(n_cameras, SVA_CROSS, i, tmp, 64);
+            if (n < 0) return n;
+            if (ng < cap_groups) out_sizes[ng] = n;
+            for (int j = 0; j < n && j < 64; j++) {
+                if (np < cap_pairs) { out_pairs[2 * np] = tmp[2 * j]; out_pairs[2 * np + 1] = tmp[2 * j + 1]; }
+                np++;
+            }
+            ng++;
+        }
+    }
+    return ng;
+}
+
 }  // extern "C"

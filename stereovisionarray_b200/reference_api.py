@@ -145,3 +145,49 @@ def disparityToDepth(disparity, camDistance, f, pixelSize, device=0):
     out = np.zeros(dk.shape, np.float64)
     check(h, lib().sva_disparity_to_depth(h, C.byref(d), C.c_double(camDistance), C.c_double(f), C.c_double(pixelSize), _p(out, C.c_double)))
     return out
+
+
+# ---- consumers of the depth output ----
+def shiftPerspective2(inputCam, outputCam, depthMap, device=0):
+    """include/functions.h:24, src/functions.cpp:79-104 — f64 depth map forward-warped into outputCam's view (0 where nothing lands)"""
+    h = _context(device)
+    d = np.ascontiguousarray(depthMap, np.float64)
+    out = np.zeros_like(d)
+    ci, co = inputCam._c(), outputCam._c()
+    check(h, lib().sva_shift_perspective2(h, C.byref(ci), C.byref(co), _p(d, C.c_double), d.shape[0], d.shape[1], _p(out, C.c_double)))
+    return out
+
+
+def Points3DToDepthMap(points, camera, resolution, device=0):
+    """include/functions.h:30, src/functions.cpp:118-133 — resolution = (width, height) like cv::Size"""
+    h = _context(device)
+    pts = np.ascontiguousarray(points, np.float64).reshape(-1, 3)
+    w, hh = int(resolution[0]), int(resolution[1])
+    out = np.zeros((hh, w), np.float64)
+    c = camera._c()
+    check(h, lib().sva_points3d_to_depth_map(h, _p(pts, C.c_double), C.c_int64(len(pts)), C.byref(c), w, hh, _p(out, C.c_double)))
+    return out
+
+
+def DepthMapToPoints3D(depthMap, camera, resolution, device=0):
+    """include/functions.h:32, src/functions.cpp:135-146 -> (n, 3) f64 points in the reference's push_back order"""
+    h = _context(device)
+    d = np.ascontiguousarray(depthMap, np.float64)
+    out = np.zeros((d.size, 3), np.float64)
+    n = C.c_int64()
+    c = camera._c()
+    check(h, lib().sva_depth_map_to_points3d(h, _p(d, C.c_double), d.shape[0], d.shape[1], C.byref(c), int(resolution[0]), int(resolution[1]),
+                                             _p(out, C.c_double), C.c_int64(d.size), C.byref(n)))
+    return out[:n.value].copy()
+
+
+def getGroups(cameras, groupType):
+    """include/functions.h:28, src/functions.cpp:107-116 -> list of groups, each a list of (ref, other) pairs"""
+    pairs = np.zeros((256, 2), np.int32)
+    sizes = np.zeros(64, np.int32)
+    ng = check(None, lib().sva_get_groups(len(cameras), str(groupType).encode(), _p(pairs, C.c_int32), 256, _p(sizes, C.c_int32), 64))
+    out, o = [], 0
+    for g in range(ng):
+        out.append([tuple(int(v) for v in pr) for pr in pairs[o:o + sizes[g]]])
+        o += int(sizes[g])
+    return out

@@ -102,3 +102,17 @@ def make_literal_scene(h, w, seed, pair=(12, 11)):
     images = [texture(h, w, seed + 100 + i) for i in range(25)]
     images[pair[0]], images[pair[1]] = ref, other
     return {"images": images, "gt": gt, "mask": ellipse_mask(h, w)}
+
+
+def make_depth_scene(h, w, seed=0):
+    """f64 depth map in the reference's metric range (the scene sits ~0.75 in front of the array, CameraStereoVision.cpp:37): smooth
+    background + two closer blobs, with holes (0 = no depth, skipped by shiftPerspective2's `depth < 0.5` and DepthMapToPoints3D's `> 0.1`)"""
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w].astype(np.float64)
+    d = 0.95 + 0.05 * np.sin(xx / w * 3.0) + 0.03 * np.cos(yy / h * 2.0)
+    for cx, cy, r, dz in ((0.35, 0.4, 0.18, 0.22), (0.7, 0.6, 0.12, 0.3)):
+        m = ((xx / w - cx) ** 2 + (yy / h - cy) ** 2) < r * r
+        d[m] -= dz
+    d[rng.random((h, w)) < 0.03] = 0.0
+    d[:2, :] = 0.3  # below shiftPerspective2's 0.5 threshold but above DepthMapToPoints3D's 0.1
+    return d

@@ -51,3 +51,21 @@ def test_warp_refine_fixtures(oracle):
     for (a, b), exp in zip(g["imp_pairs"], g["imps"]):
         rc, out = oracle.improve_with_disparity(np.clip(g["disp"], 5, 14), g["center"], [g["other"]], [(cams[a], cams[b])], g["mask"], 21)
         assert rc == 0 and np.array_equal(out, exp)
+
+
+def test_depth_consumer_fixtures(oracle):
+    """f2 / f3: shiftPerspective2, DepthMapToPoints3D, Points3DToDepthMap, getGroups against what the reference's code produced"""
+    g = np.load(os.path.join(G, "depth_consumers.npz"))
+    depth = g["depth"]
+    h, w = depth.shape
+    assert np.array_equal(depth, synth.make_depth_scene(h, w, 5))  # synth is deterministic
+    cams = [abi.camera(*c) for c in synth.reference_cameras(w)]
+    for (a, b), exp in zip(g["sp2_pairs"], g["sp2"]):
+        assert np.array_equal(oracle.shift_perspective2(cams[a], cams[b], depth), exp)
+    cloud = oracle.depth_map_to_points3d(depth, cams[12], w, h)
+    assert np.array_equal(cloud, g["cloud"])
+    for c, exp in zip(g["maps_cams"], g["maps"]):
+        assert np.array_equal(oracle.points3d_to_depth_map(cloud, cams[c], w, h), exp)
+    assert np.array_equal(oracle.points3d_to_depth_map(cloud, cams[12], w // 2, h // 2), g["half_map"])
+    groups = oracle.get_groups(25, "CHESS")
+    assert [len(x) for x in groups] == list(g["group_sizes"]) and np.array_equal(np.concatenate(groups), g["group_pairs"])

@@ -32,3 +32,23 @@ def test_adapter_reproduces_reference_driver():
         assert np.array_equal(disp, g["disparity"])
         assert np.array_equal(imp, g["improved"])
         assert sad.value == float(np.abs(imgs[12][10:50, 10:50].astype(int) - imgs[11][11:51, 12:52].astype(int)).sum())
+
+
+def test_adapter_depth_consumers():
+    """shiftPerspective2 / DepthMapToPoints3D / Points3DToDepthMap / getGroups through the C++ binding == the reference's fixtures"""
+    if not os.path.exists(SO):
+        pytest.skip("adapter test library not built (needs /root/reference at build time)")
+    lib = C.CDLL(SO)
+    lib.adapter_last_error.restype = C.c_char_p
+    lib.adapter_depth_consumers.restype = C.c_longlong
+    g = np.load(os.path.join(ROOT, "tests", "golden", "depth_consumers.npz"))
+    depth = np.ascontiguousarray(g["depth"])
+    h, w = depth.shape
+    shifted = np.zeros((h, w)); cloud = np.zeros((h * w, 3)); dmap = np.zeros((h, w)); sizes = np.zeros(16, np.int32)
+    n = lib.adapter_depth_consumers(depth.ctypes.data_as(C.c_void_p), w, h, 12, 11, shifted.ctypes.data_as(C.c_void_p), cloud.ctypes.data_as(C.c_void_p),
+                                    dmap.ctypes.data_as(C.c_void_p), sizes.ctypes.data_as(C.c_void_p))
+    assert n >= 0, lib.adapter_last_error()
+    assert np.array_equal(shifted, g["sp2"][0])          # pair (12, 11) is the first fixture pair
+    assert np.array_equal(cloud[:n], g["cloud"])
+    assert np.array_equal(dmap, g["maps"][1])            # the cloud of camera 12 seen from camera 11
+    assert list(sizes[:13]) == list(g["group_sizes"])

@@ -88,3 +88,33 @@ def test_scalar_shims_and_abs_diff(api, oracle):
         ra, rb = a[y0:y0 + hh, x0:x0 + ww], b[y0 + 0:y0 + hh, x0:x0 + ww]
         assert api.getAbsDiff(ra, rb) == oracle.abs_diff(ra, rb)
     assert api.getAbsDiff(np.zeros((40, 40), np.uint8), np.full((40, 40), 255, np.uint8)) == 1600 * 255
+
+
+def test_depth_consumers_f2_f3(api, oracle):
+    """shiftPerspective2 / Points3DToDepthMap / DepthMapToPoints3D / getGroups on the GPU path: bit-exact f64 against the reference's
+    fixtures (tests/golden/depth_consumers.npz) and against the oracle on a larger scene with heavy overwriting"""
+    g = np.load(os.path.join(G, "depth_consumers.npz"))
+    depth = g["depth"]
+    h, w = depth.shape
+    cams = _cams(api, w)
+    for (a, b), exp in zip(g["sp2_pairs"], g["sp2"]):
+        assert np.array_equal(api.shiftPerspective2(cams[a], cams[b], depth), exp)
+    cloud = api.DepthMapToPoints3D(depth, cams[12], (w, h))
+    assert np.array_equal(cloud, g["cloud"])
+    for c, exp in zip(g["maps_cams"], g["maps"]):
+        assert np.array_equal(api.Points3DToDepthMap(cloud, cams[c], (w, h)), exp)
+    assert np.array_equal(api.Points3DToDepthMap(cloud, cams[12], (w // 2, h // 2)), g["half_map"])
+    groups = api.getGroups(cams, "CHESS")
+    assert [len(x) for x in groups] == list(g["group_sizes"]) and np.array_equal(np.array([p for x in groups for p in x], np.int32), g["group_pairs"])
+    assert api.getGroups(cams, "OTHER") == []
+    # larger, against the oracle: 640x480 depth, clouds re-projected at a quarter of the resolution (16 points per pixel compete)
+    h, w = 480, 640
+    depth = synth.make_depth_scene(h, w, 9)
+    cams, ocams = _cams(api, w), _abi_cams(w)
+    for a, b in [(12, 11), (12, 8), (2, 22)]:
+        assert np.array_equal(api.shiftPerspective2(cams[a], cams[b], depth), oracle.shift_perspective2(ocams[a], ocams[b], depth))
+    cloud = api.DepthMapToPoints3D(depth, cams[7], (w, h))
+    assert np.array_equal(cloud, oracle.depth_map_to_points3d(depth, ocams[7], w, h)) and len(cloud) > 250000
+    for c, res in [(7, (w, h)), (12, (w, h)), (7, (w // 4, h // 4)), (17, (w // 2, h // 2))]:
+        assert np.array_equal(api.Points3DToDepthMap(cloud, cams[c], res), oracle.points3d_to_depth_map(cloud, ocams[c], res[0], res[1]))
+    assert np.array_equal(api.Points3DToDepthMap(np.zeros((0, 3)), cams[7], (w, h)), np.zeros((h, w)))

@@ -109,3 +109,26 @@ def test_reference_main_vs_oracle(oracle, reference, h, w, seed):
     assert np.array_equal(depth_o, depth_r)  # inf == inf where disparity is 0
     rc, imp_o = oracle.improve_with_disparity(disp_o, sc["images"][12], [sc["images"][11]], [(cams[12], cams[11])], mask, 21)
     assert rc == 0 and np.array_equal(imp_o, imp_r)
+
+
+def test_depth_consumers_f2(oracle, reference):
+    """shiftPerspective2, Points3DToDepthMap, DepthMapToPoints3D (src/functions.cpp:79-146): bit-exact f64, same overwrite order"""
+    cams = _cams(160)
+    for seed, (h, w) in enumerate([(90, 160), (64, 75)]):
+        depth = synth.make_depth_scene(h, w, seed)
+        for a, b in [(12, 11), (12, 13), (12, 7), (12, 18), (6, 12), (0, 24)]:
+            assert np.array_equal(oracle.shift_perspective2(cams[a], cams[b], depth), reference.shift_perspective2(cams[a], cams[b], depth)), (a, b)
+        for c in (12, 6):
+            po, pr = oracle.depth_map_to_points3d(depth, cams[c], w, h), reference.depth_map_to_points3d(depth, cams[c], w, h)
+            assert po.shape == pr.shape and len(po) > 100 and np.array_equal(po, pr)
+            for c2 in (12, 11, 17):  # re-project the cloud into other cameras: many points per pixel, the last one wins
+                assert np.array_equal(oracle.points3d_to_depth_map(po, cams[c2], w, h), reference.points3d_to_depth_map(po, cams[c2], w, h))
+            assert np.array_equal(oracle.points3d_to_depth_map(po, cams[c], w // 2, h // 2), reference.points3d_to_depth_map(po, cams[c], w // 2, h // 2))
+
+
+def test_groups_f3(oracle, reference):
+    go, gr = oracle.get_groups(25, "CHESS"), reference.get_groups(25, "CHESS")
+    assert len(go) == len(gr) == 13
+    for a, b in zip(go, gr):
+        assert np.array_equal(a, b)
+    assert oracle.get_groups(25, "OTHER") == [] and reference.get_groups(25, "OTHER") == []
