@@ -139,6 +139,15 @@ int sva_depth_map_to_points3d(sva_ctx* ctx, const double* depth, int32_t rows, i
 /* getGroups — include/functions.h:28, src/functions.cpp:107-116.  Returns the number of groups. */
 int sva_get_groups(int32_t n_cameras, const char* group_type, int32_t* out_pairs, int32_t cap_pairs, int32_t* out_sizes, int32_t cap_groups);
 
+/* ---- ingest ---------------------------------------------------------------------------------------------------------- */
+/* resize(img, img, Size(), 0.5, 0.5) — src/CameraStereoVision.cpp:18 (default INTER_LINEAR; for the exact 2x decimation of an even-sized
+ * u8 image that is the rounded mean of each 2x2 block).  out: rows/2 x cols/2, tight pitch.  Odd sizes are rejected. */
+int sva_resize_half_u8(sva_ctx* ctx, const sva_image_u8* img, uint8_t* out);
+/* cv::FileStorage YAML matrices — saveImage / loadImage (key "image") and getIdealRef (key "R"), src/functions.cpp:323-346.
+ * dtype 0 = u8, 1 = f64, single channel.  read: out == NULL only queries rows / cols / dtype.  Host side, no GPU work. */
+int sva_yaml_write_matrix(const char* path, const char* name, const void* data, int32_t rows, int32_t cols, int32_t dtype);
+int sva_yaml_read_matrix(const char* path, const char* name, void* out, int64_t cap_bytes, int32_t* rows, int32_t* cols, int32_t* dtype);
+
 /* The whole volume-mode pipeline (cost volume -> SGM -> WTA/LR/sub-pixel), DESIGN.md §3.
  * others[n_pairs] are the other views in pair order.  out_disp: u16 (min_disp + d, SVA_DISP_INVALID when rejected);
  * out_subpix (may be NULL): f32. */

@@ -191,3 +191,54 @@ def getGroups(cameras, groupType):
         out.append([tuple(int(v) for v in pr) for pr in pairs[o:o + sizes[g]]])
         o += int(sizes[g])
     return out
+
+
+# ---- ingest ----
+def resizeHalf(image, device=0):
+    """resize(img, img, Size(), 0.5, 0.5) of the driver's loader (src/CameraStereoVision.cpp:18) for even-sized u8 images, on the GPU"""
+    h = _context(device)
+    im, keep = abi.image_u8(np.ascontiguousarray(image, np.uint8))
+    out = np.zeros((keep.shape[0] // 2, keep.shape[1] // 2), np.uint8)
+    check(h, lib().sva_resize_half_u8(h, C.byref(im), _p(out, C.c_uint8)))
+    return out
+
+
+def _yaml_write(filename, name, image):
+    a = np.ascontiguousarray(image)
+    if a.ndim != 2 or a.dtype not in (np.uint8, np.float64):
+        raise CvException("only single-channel u8 / f64 matrices are supported")
+    rc = lib().sva_yaml_write_matrix(str(filename).encode(), name.encode(), a.ctypes.data_as(C.c_void_p), a.shape[0], a.shape[1], 0 if a.dtype == np.uint8 else 1)
+    if rc != 0:
+        raise CvException("cannot write %s" % filename)
+
+
+def _yaml_read(filename, name):
+    r, c, t = C.c_int32(), C.c_int32(), C.c_int32()
+    if lib().sva_yaml_read_matrix(str(filename).encode(), name.encode(), None, C.c_int64(0), C.byref(r), C.byref(c), C.byref(t)) != 0:
+        return np.zeros((0, 0), np.uint8)  # the reference returns an empty Mat for a missing file / key
+    out = np.zeros((r.value, c.value), np.uint8 if t.value == 0 else np.float64)
+    if lib().sva_yaml_read_matrix(str(filename).encode(), name.encode(), out.ctypes.data_as(C.c_void_p), C.c_int64(out.nbytes), C.byref(r), C.byref(c), C.byref(t)) != 0:
+        raise CvException("malformed matrix in %s" % filename)
+    return out
+
+
+def saveImage(filename, image):
+    """include/functions.h:49, src/functions.cpp:332-338 — cv::FileStorage YAML under the key `image`"""
+    _yaml_write(filename, "image", image)
+
+
+def loadImage(filename):
+    """include/functions.h:51, src/functions.cpp:340-346"""
+    return _yaml_read(filename, "image")
+
+
+def getIdealRef(filename="idealRef.yml"):
+    """include/functions.h:47, src/functions.cpp:323-330 — the ground-truth depth map under the key `R`"""
+    return _yaml_read(filename, "R")
+
+
+def getImagesPathsFromFolder(folderPath):
+    """include/functions.h:43, src/functions.cpp:241-251 — directory order, like std::filesystem::directory_iterator"""
+    import os
+    with os.scandir(folderPath) as it:
+        return [e.path for e in it]
