@@ -136,6 +136,9 @@ int sva_points3d_to_depth_map(sva_ctx* ctx, const double* points_xyz, int64_t n_
  * *out_count = number of points; at most `cap` are written. */
 int sva_depth_map_to_points3d(sva_ctx* ctx, const double* depth, int32_t rows, int32_t cols, const sva_camera* cam, int32_t width, int32_t height,
                               double* out_xyz, int64_t cap, int64_t* out_count);
+/* calculateAverageError — include/functions.h:53, src/functions.cpp:348-354: cv::mean(image, mask)[0] of an f64 map (0 for an empty mask).
+ * Deterministic summation order; equal to any other order within a few ulp. */
+int sva_masked_mean_f64(sva_ctx* ctx, const double* image, int32_t rows, int32_t cols, const sva_image_u8* mask, double* out_mean);
 /* getGroups — include/functions.h:28, src/functions.cpp:107-116.  Returns the number of groups. */
 int sva_get_groups(int32_t n_cameras, const char* group_type, int32_t* out_pairs, int32_t cap_pairs, int32_t* out_sizes, int32_t cap_groups);
 

@@ -15,7 +15,7 @@ EXPORTS = [
     "sva_camera_project", "sva_camera_inv_project", "sva_bresenham", "sva_get_camera_pairs", "sva_grid_pairs",
     "sva_abs_diff_u8", "sva_match_literal", "sva_shift_perspective_with_disparity", "sva_improve_with_disparity",
     "sva_resize_half_u8", "sva_yaml_write_matrix", "sva_yaml_read_matrix",
-    "sva_shift_perspective2", "sva_points3d_to_depth_map", "sva_depth_map_to_points3d", "sva_get_groups",
+    "sva_shift_perspective2", "sva_points3d_to_depth_map", "sva_depth_map_to_points3d", "sva_get_groups", "sva_masked_mean_f64",
     "sva_disparity_to_depth", "sva_depth_from_array", "sva_stream_submit", "sva_stream_wait", "sva_stream_mark", "sva_stream_elapsed",
     "sva_frame_upload", "sva_frame_set_pair_range", "sva_frame_run", "sva_frame_time", "sva_frame_kernel_times", "sva_frame_time_detailed", "sva_timer_start", "sva_timer_stop", "sva_frame_set_debug",
     "sva_frame_download_ad", "sva_frame_download_cost", "sva_frame_download_raw_cost", "sva_frame_download_sgm",

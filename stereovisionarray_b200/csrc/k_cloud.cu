@@ -73,6 +73,26 @@ __global__ void k_d2p_scatter(const double* __restrict__ depth, int rows, int co
     o[0] = __dadd_rn(c.px, __dmul_rn(rx, d)); o[1] = __dadd_rn(c.py, __dmul_rn(ry, d)); o[2] = __dadd_rn(c.pz, __dmul_rn(rz, d));
 }
 
+// ---- calculateAverageError — src/functions.cpp:348-354: cv::mean(image, mask)[0] ----
+// per-block partial sums in a fixed order (thread-strided, then a shared-memory tree), block partials added on the host in block order:
+// deterministic, and within a few ulp of any other summation order (cv::mean's own blocking is not specified)
+__global__ void k_masked_sum(const double* __restrict__ img, const uint8_t* __restrict__ mask, size_t n, double* __restrict__ part_sum,
+                             unsigned long long* __restrict__ part_cnt) {
+    __shared__ double s_sum[256];
+    __shared__ unsigned long long s_cnt[256];
+    double acc = 0.0;
+    unsigned long long cnt = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        if (mask[i]) { acc = __dadd_rn(acc, img[i]); cnt++; }
+    s_sum[threadIdx.x] = acc; s_cnt[threadIdx.x] = cnt;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s_sum[threadIdx.x] = __dadd_rn(s_sum[threadIdx.x], s_sum[threadIdx.x + o]); s_cnt[threadIdx.x] += s_cnt[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { part_sum[blockIdx.x] = s_sum[0]; part_cnt[blockIdx.x] = s_cnt[0]; }
+}
+
 static DevCam dev_cam(const sva_camera* c) { return DevCam{c->pos[0], c->pos[1], c->pos[2], c->f, c->pixel_size}; }
 
 extern "C" {
@@ -158,6 +178,34 @@ int sva_depth_map_to_points3d(sva_ctx* c, const double* depth, int32_t rows, int
         SVA_CUDA_OK(c, cudaMemcpyAsync(out_xyz, d_pts, (size_t)wr * 24, cudaMemcpyDeviceToHost, c->stream));
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     }
+    return SVA_OK;
+}
+
+int sva_masked_mean_f64(sva_ctx* c, const double* image, int32_t rows, int32_t cols, const sva_image_u8* mask, double* out_mean) {
+    if (!c || !image || !mask || !mask->data || !out_mean || rows < 1 || cols < 1 || mask->rows != rows || mask->cols != cols || mask->step < (size_t)cols)
+        return c ? c->fail(SVA_ERR_BAD_ARG, "masked_mean: bad argument") : SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    const size_t n = (size_t)rows * cols;
+    const int blocks = 296;
+    SVA_TRY(c->reserve(c->scratch, n * 8 + n + 64));
+    SVA_TRY(c->reserve(c->scratch2, (size_t)blocks * 16));
+    double* d_img = c->scratch.as<double>();
+    uint8_t* d_mask = reinterpret_cast<uint8_t*>(d_img + n);
+    double* d_sum = c->scratch2.as<double>();
+    unsigned long long* d_cnt = reinterpret_cast<unsigned long long*>(d_sum + blocks);
+    SVA_CUDA_OK(c, cudaMemcpyAsync(d_img, image, n * 8, cudaMemcpyHostToDevice, c->stream));
+    SVA_CUDA_OK(c, cudaMemcpy2DAsync(d_mask, cols, mask->data, mask->step, cols, rows, cudaMemcpyHostToDevice, c->stream));
+    { LaunchScope ls(c, "k_masked_sum"); k_masked_sum<<<blocks, 256, 0, c->stream>>>(d_img, d_mask, n, d_sum, d_cnt); }
+    SVA_CUDA_OK(c, cudaGetLastError());
+    std::vector<double> hs(blocks);
+    std::vector<unsigned long long> hc(blocks);
+    SVA_CUDA_OK(c, cudaMemcpyAsync(hs.data(), d_sum, blocks * 8, cudaMemcpyDeviceToHost, c->stream));
+    SVA_CUDA_OK(c, cudaMemcpyAsync(hc.data(), d_cnt, blocks * 8, cudaMemcpyDeviceToHost, c->stream));
+    SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    double sum = 0.0;
+    unsigned long long cnt = 0;
+    for (int i = 0; i < blocks; i++) { sum += hs[i]; cnt += hc[i]; }
+    *out_mean = cnt ? sum / (double)cnt : 0.0;  // cv::mean of an empty mask is 0
     return SVA_OK;
 }
 

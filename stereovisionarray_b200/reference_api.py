@@ -181,6 +181,16 @@ def DepthMapToPoints3D(depthMap, camera, resolution, device=0):
     return out[:n.value].copy()
 
 
+def calculateAverageError(image, mask, device=0):
+    """include/functions.h:53, src/functions.cpp:348-354 — mean of an f64 error / depth map under the face mask (the mask is an input here)"""
+    h = _context(device)
+    a = np.ascontiguousarray(image, np.float64)
+    m, mk = abi.image_u8(np.ascontiguousarray(mask, np.uint8))
+    out = C.c_double()
+    check(h, lib().sva_masked_mean_f64(h, _p(a, C.c_double), a.shape[0], a.shape[1], C.byref(m), C.byref(out)))
+    return out.value
+
+
 def getGroups(cameras, groupType):
     """include/functions.h:28, src/functions.cpp:107-116 -> list of groups, each a list of (ref, other) pairs"""
     pairs = np.zeros((256, 2), np.int32)

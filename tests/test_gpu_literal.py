@@ -118,3 +118,14 @@ def test_depth_consumers_f2_f3(api, oracle):
     for c, res in [(7, (w, h)), (12, (w, h)), (7, (w // 4, h // 4)), (17, (w // 2, h // 2))]:
         assert np.array_equal(api.Points3DToDepthMap(cloud, cams[c], res), oracle.points3d_to_depth_map(cloud, ocams[c], res[0], res[1]))
     assert np.array_equal(api.Points3DToDepthMap(np.zeros((0, 3)), cams[7], (w, h)), np.zeros((h, w)))
+
+
+def test_calculate_average_error(api):
+    """cv::mean(image, mask)[0] (src/functions.cpp:348-354): the masked mean of an f64 map, against numpy and cv2"""
+    import cv2
+    rng = np.random.default_rng(8)
+    img = rng.random((480, 640)) * 2.0 - 0.5
+    mask = synth.ellipse_mask(480, 640)
+    got = api.calculateAverageError(img, mask)
+    assert abs(got - float(img[mask != 0].mean())) <= 1e-13 and abs(got - cv2.mean(img, mask)[0]) <= 1e-13
+    assert api.calculateAverageError(img, np.zeros_like(mask)) == 0.0 == cv2.mean(img, np.zeros_like(mask))[0]
