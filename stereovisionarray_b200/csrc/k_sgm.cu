@@ -24,6 +24,7 @@
 // gives the first-minimum winner; S(d*-1), S(d*+1) are fetched with two shuffles for the parabola; the other view's WTA
 // (left-right check) is a systolic diagonal minimum: one key register per disparity slot shifts by one slot per step.
 #include <algorithm>
+#include <cstdio>
 #include <cstdlib>
 
 #include "sva_common.cuh"
@@ -53,6 +54,7 @@ struct SgmParams {
     unsigned int* pace_arrive;  // k_sgm_acc: [pace_rounds] CTAs that finished round r (nullptr = no global pacing)
     unsigned int* pace_min;     // rounds finished by every CTA
     int pace_rounds, pace_window, march_warps;
+    int diag_split;     // k_sgm_acc, one line per warp: diagonals run the event-split march (SVA_SGM_DIAG_SPLIT, default on)
     int c_ds;           // 0: C is [H][W][D]; > 0: C is slice-major [D / c_ds][H][W][c_ds] (disparity slices gathered from several GPUs)
     int exp_no_out;     // timing experiment only (SVA_SGM_EXP=1): run the recurrence but drop the S updates
     int cta_sync;       // k_sgm_acc (balanced): named barrier among the row-sweeping warps of a CTA every round
@@ -395,8 +397,95 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     for (int s = s0; s < len; s++) step(ring + (s % NS) * STAGE, ring + ((s + PF) % NS) * STAGE, s + PF < len);
 }
 
+// Diagonal march for ONE line per warp, split at the wrap events.  A diagonal leaves the image sideways once every W steps; the
+// prefetch cursor does so PF steps before the accumulate cursor.  Between two such events nothing special happens, so the step body
+// carries no wrap / restart logic at all (in the generic march that logic is ~8 predicated integer instructions per step on a kernel
+// bound by the integer pipe): whole ring rounds of NS steps run unrolled, the few steps around an event run one at a time.  The wrap
+// step is a per-line constant, i.e. warp-uniform here.  The CTA barrier / pacing rhythm (every NS steps, same step indices in every
+// warp) is kept, so the warps of a CTA still meet the same number of times.
+template <int NR, int PF, bool FULL, bool STORE>
+__device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const int dx, const int dy, const int line, const bool do_out, const int lane,
+                                                     const uint32_t ring, const int bar_threads, volatile int* s_pace, const bool leader) {
+    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
+    const int W = q.W, H = q.H, D = q.D;
+    const int len = H;
+    const int x0 = line, y0 = dy > 0 ? 0 : H - 1;
+    const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
+    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lane * NV);
+    const int cds = q.c_ds > 0 ? q.c_ds : D;
+    const uint32_t dstep_c = (uint32_t)((dy * W + dx) * cds), wrapfix_c = (uint32_t)(-dx * W * cds);
+    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lane * NV) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lane * NV) % cds) : start;
+    uint32_t ic = start_c, is = start;
+    const bool active = FULL || lane < q.lanes;
+    const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
+    int wc = dx > 0 ? W - x0 : x0 + 1;  // the prefetch cursor wraps after this many advances ...
+    int ws = wc;                        // ... the accumulate cursor after this many (then every W more)
+    int adv_c = 0;
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        if (u < len) {
+            if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic);
+            ic += dstep_c;
+            if (++adv_c == wc) { ic += wrapfix_c; wc += W; }
+        }
+        cp_async_commit();
+    }
+    uint32_t L[NR];
+#pragma unroll
+    for (int j = 0; j < NR; j++) L[j] = 0;
+    uint32_t mm = 0, mp2 = q.p2p2;
+    auto step = [&](const uint32_t slot_addr, const uint32_t refill_addr, const bool refill) {
+        cp_async_wait<PF - 1>();
+        uint32_t Cc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
+        if (active) Vec<NR>::lds(slot_addr, Cc);
+        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); ic += dstep_c; }
+        cp_async_commit();
+        sgm_step<NR, 32>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+        if (active && do_out) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
+        is += dstep;
+    };
+    int s = 0, slot = 0, round = 0;
+    while (s < len) {
+        // last step before the next event: the prefetch cursor has advanced PF + s + 1 times after step s (while it refills)
+        const int e_c = wc - PF - 1, e_s = ws - 1;
+        const int e = min(len - 1, min(e_c, e_s));
+        while (s <= e) {
+            const bool paced = slot == 0 && s + NS + PF <= len;
+            if (paced && bar_threads) {
+                asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+                if (s_pace) {
+                    if (leader && lane == 0) s_pace[0] = round;
+                    for (int spin = 0; spin < 4096 && round > s_pace[1] + q.pace_window; spin++) __nanosleep(128);
+                }
+            }
+            if (paced) round++;
+            if (paced && s + NS - 1 <= e) {  // a whole ring round without an event: every step refills
+#pragma unroll
+                for (int u = 0; u < NS; u++) step(ring + u * STAGE, ring + ((u + PF) % NS) * STAGE, true);
+                s += NS;
+            } else {
+                const int rs = slot + PF >= NS ? slot + PF - NS : slot + PF;
+                step(ring + slot * STAGE, ring + rs * STAGE, s + PF < len);
+                s++;
+                slot = slot + 1 == NS ? 0 : slot + 1;
+            }
+        }
+        if (e == e_c) { ic += wrapfix_c; wc += W; }
+        if (e == e_s) {  // the next cell starts a fresh path: L = C
+            is += wrapfix; ws += W;
+#pragma unroll
+            for (int j = 0; j < NR; j++) L[j] = 0;
+            mm = 0; mp2 = q.p2p2;
+        }
+    }
+    if (s_pace && leader && lane == 0) s_pace[0] = round;  // all paced rounds done (lets the helper warp finish)
+}
+
+// 40 registers: 48 resident warps per SM (e.g. two 22-warp CTAs of a paced c4 launch) must fit the 64 K register file
 template <int NR, int PF, bool FULL, bool STORE, int LPL>
-__global__ void __launch_bounds__(1024)
+__global__ void __maxnreg__(LPL == 32 && NR <= 4 ? 40 : 64)
 k_sgm_acc(SgmParams q) {
     constexpr int LPW = 32 / LPL;  // path lines per warp
     constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
@@ -449,8 +538,10 @@ k_sgm_acc(SgmParams q) {
         leader = warp == first;
     }
     volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
-    if (dx != 0 && dy != 0) sgm_acc_march<NR, PF, FULL, true, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
-    else sgm_acc_march<NR, PF, FULL, false, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
+    if (dx != 0 && dy != 0) {
+        if (LPL == 32 && q.diag_split) sgm_acc_march_diag32<NR, PF, FULL, STORE>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
+        else sgm_acc_march<NR, PF, FULL, true, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
+    } else sgm_acc_march<NR, PF, FULL, false, STORE, LPL>(q, dx, dy, line, do_out, lane, ring, bar_threads, pace, leader);
 }
 
 template <int NR, int PF, bool FULL, bool STORE, int LPL>
@@ -460,6 +551,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines_all, size_t r
     SgmParams qq = q;
     qq.balanced = 0;
     qq.cta_sync = ctx->tune_sgm_cta_sync;
+    qq.diag_split = ctx->tune_sgm_diag_split;
     if (ctx->tune_sgm_balanced) {
         // one wave of identical CTAs: m CTAs per SM, as few warps per CTA as cover all lines
         for (int m = 1; m <= 8; m++) {
@@ -480,6 +572,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines_all, size_t r
         // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
         int per_sm = 0;
         SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, LPL>, threads + 32, smem));
+        if (getenv("SVA_DEBUG")) fprintf(stderr, "[sva] sgm_acc NR=%d ndirs=%d grid=%d threads=%d smem=%zu per_sm=%d\n", NR, q.ndirs, grid, threads + 32, smem, per_sm);
         if ((long long)per_sm * ctx->sm_count >= grid) {
             const int rounds = (q.H - PF) / (PF + 1);
             if (rounds > ctx->tune_sgm_pace_window) {
@@ -493,6 +586,9 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, int nlines_all, size_t r
             }
         }
     }
+    // measured: the event-split diagonal march gains 6.6 % on unpaced launches (c1: 0.279 -> 0.261 ms) and nothing on paced ones (c2 / c4
+    // move at the pace of the grid-wide minimum), where the generic march is kept
+    if (qq.pace_arrive && ctx->tune_sgm_diag_split < 2) qq.diag_split = 0;
     LaunchScope ls(ctx, name);
     k_sgm_acc<NR, PF, FULL, STORE, LPL><<<grid, threads, smem, ctx->stream>>>(qq);
     return SVA_OK;

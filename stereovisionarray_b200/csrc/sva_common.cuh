@@ -99,6 +99,7 @@ struct sva_ctx {
     int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
     int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
     int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
+    int tune_sgm_diag_split = 1;  // SVA_SGM_DIAG_SPLIT: diagonal lines run the march that is split at the wrap events (no per-step wrap logic)
     int tune_sgm_overlap = 0;     // SVA_SGM_OVERLAP (experiments, off): 1 = horizontal launch on a second stream next to the row-sweeping ones, 2 = up next to down.
                                   // Measured on B200 at c1: no gain either way (1.53 ms per frame in all three) — the launches contend for the same issue slots / L2 REDs
     int tune_sgm_lpl = 32;        // SVA_SGM_LPL: lanes per path line in the accumulate passes (32 = one line per warp, 16 / 8 = two / four)

@@ -74,6 +74,7 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_LPL")) c->tune_sgm_lpl = atoi(e);
     if (const char* e = getenv("SVA_SGM_OVERLAP")) c->tune_sgm_overlap = atoi(e);
     if (const char* e = getenv("SVA_PREZERO")) c->tune_prezero = atoi(e);
+    if (const char* e = getenv("SVA_SGM_DIAG_SPLIT")) c->tune_sgm_diag_split = atoi(e);
     if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
     if (const char* e = getenv("SVA_AD_GATHER")) c->tune_ad_gather = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE_WINDOW")) c->tune_sgm_pace_window = atoi(e);
