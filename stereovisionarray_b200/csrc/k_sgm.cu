@@ -67,13 +67,19 @@ struct SgmParams {
 // one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
 // LPL = lanes per path line: 32 (one line per warp) or 16 / 8 (two / four lines per warp — more cells per lane, so the
 // shuffles, the minimum reduction and the loop overhead are amortised over more cells)
-template <int NR, int LPL = 32>
+// EDGE_BIAS (every lane of the group active): instead of replacing the missing d-1 / d+1 neighbour of the first / last disparity by
+// +inf with two selects per step, the lane adds a per-lane P1 whose edge half is 0x7FFF (p1_up, p1_dn): the neighbour slot then holds a
+// bounded real value (<= 8190), 8190 + 0x7FFF < 2^16 does not wrap and is larger than every real cost, so the minimum ignores it.
+template <int NR, int LPL = 32, bool EDGE_BIAS = false>
 __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)[NR], uint32_t& mm, uint32_t& mp2, uint32_t p1p1, uint32_t p2p2,
-                                         bool first_lane, bool last_lane) {
+                                         bool first_lane, bool last_lane, uint32_t p1_up = 0, uint32_t p1_dn = 0) {
     uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1, LPL);
     uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1, LPL);
-    if (first_lane) up = SGM_INF2;
-    if (last_lane) dn = SGM_INF2;
+    if (!EDGE_BIAS) {
+        if (first_lane) up = SGM_INF2;
+        if (last_lane) dn = SGM_INF2;
+        p1_up = p1p1; p1_dn = p1p1;
+    }
     uint32_t sh[NR + 1];  // sh[j] = values at d-1 of register j; sh[j+1] = values at d+1 of register j
     sh[0] = __byte_perm(up, L[0], 0x5432);
 #pragma unroll
@@ -82,8 +88,8 @@ __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)
     uint32_t mloc = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-        uint32_t t = __viaddmin_u16x2(sh[j], p1p1, L[j]);
-        t = __viaddmin_u16x2(sh[j + 1], p1p1, t);
+        uint32_t t = __viaddmin_u16x2(sh[j], j == 0 ? p1_up : p1p1, L[j]);
+        t = __viaddmin_u16x2(sh[j + 1], j == NR - 1 ? p1_dn : p1p1, t);
         t = __vminu2(t, mp2);
         L[j] = Cc[j] + t - mm;  // both halves: t >= mm, no borrow; C + t - mm <= 8190, no carry
         mloc = __vminu2(mloc, L[j]);
@@ -342,6 +348,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     int cc = dx > 0 ? W - x0 : x0 + 1, cs = cc;       // steps until each cursor leaves the image sideways
     const bool active = FULL || lin < q.lanes;
     const bool first_lane = lin == 0, last_lane = FULL ? lin == LPL - 1 : lin == q.lanes - 1;
+    const uint32_t p1_up = first_lane ? (q.p1p1 & 0xFFFF0000u) | 0x7FFFu : q.p1p1, p1_dn = last_lane ? (q.p1p1 & 0x0000FFFFu) | 0x7FFF0000u : q.p1p1;
     auto adv = [&](uint32_t& i, int& cnt, const uint32_t step, const uint32_t fix) -> bool {
         i += step;
         if (DIAG) {
@@ -372,7 +379,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
             for (int j = 0; j < NR; j++) L[j] = 0;
             mm = 0; mp2 = q.p2p2;
         }
-        sgm_step<NR, LPL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+        sgm_step<NR, LPL, FULL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
         if (active && do_out) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
         restart = adv(is, cs, dstep, wrapfix);
     };
@@ -418,6 +425,7 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
     uint32_t ic = start_c, is = start;
     const bool active = FULL || lane < q.lanes;
     const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
+    const uint32_t p1_up = first_lane ? (q.p1p1 & 0xFFFF0000u) | 0x7FFFu : q.p1p1, p1_dn = last_lane ? (q.p1p1 & 0x0000FFFFu) | 0x7FFF0000u : q.p1p1;
     int wc = dx > 0 ? W - x0 : x0 + 1;  // the prefetch cursor wraps after this many advances ...
     int ws = wc;                        // ... the accumulate cursor after this many (then every W more)
     int adv_c = 0;
@@ -442,7 +450,7 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
         if (active) Vec<NR>::lds(slot_addr, Cc);
         if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); ic += dstep_c; }
         cp_async_commit();
-        sgm_step<NR, 32>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane);
+        sgm_step<NR, 32, FULL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
         if (active && do_out) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
         is += dstep;
     };
