@@ -87,6 +87,11 @@ int sva_set_stream(sva_ctx* ctx, void* cuda_stream); /* run on a caller stream (
 int sva_use_own_stream(sva_ctx* ctx);                 /* back to the ctx's own non-blocking stream */
 int sva_synchronize(sva_ctx* ctx);
 int sva_kernel_launches(const sva_ctx* ctx, uint64_t* out_count); /* kernels launched by this ctx so far */
+/* Self-check for boxes without compute-sanitizer: device buffers allocated after sva_debug_set_guard(ctx, 1) carry 256 KiB canary bands
+ * on both sides and a poisoned (0xCD) payload; sva_debug_check_guards synchronises the device and reports how many buffers are guarded
+ * and how many canary bytes were overwritten (any value > 0 is an out-of-bounds write by one of the library's kernels). */
+int sva_debug_set_guard(sva_ctx* ctx, int on);
+int sva_debug_check_guards(sva_ctx* ctx, int64_t* guarded_buffers, int64_t* bad_bytes);
 
 /* ---- 1:1 shims of the reference's scalar helpers (host side, no GPU work) ------------------------------------ */
 /* Camera::project — src/Camera.cpp:15-22 */

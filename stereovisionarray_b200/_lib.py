@@ -12,6 +12,7 @@ LIB_PATH = os.path.join(HERE, "libsva_b200.so")
 # every symbol include/sva_c_api.h declares (checked by tests/test_abi.py against the header text)
 EXPORTS = [
     "sva_create", "sva_destroy", "sva_last_error", "sva_api_version", "sva_set_stream", "sva_use_own_stream", "sva_synchronize", "sva_kernel_launches",
+    "sva_debug_set_guard", "sva_debug_check_guards",
     "sva_camera_project", "sva_camera_inv_project", "sva_bresenham", "sva_get_camera_pairs", "sva_grid_pairs",
     "sva_abs_diff_u8", "sva_match_literal", "sva_shift_perspective_with_disparity", "sva_improve_with_disparity",
     "sva_resize_half_u8", "sva_yaml_write_matrix", "sva_yaml_read_matrix",

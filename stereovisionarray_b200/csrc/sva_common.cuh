@@ -24,6 +24,7 @@
 struct DevBuf {
     void* p = nullptr;
     size_t bytes = 0;
+    void* base = nullptr;  // start of the allocation when it carries guard bands (sva_debug_set_guard), else null
     template <typename T> T* as() const { return (T*)p; }
 };
 
@@ -116,6 +117,9 @@ struct sva_ctx {
     ApGeom ap;
     uint64_t ap_zero_key = 0;  // geometry + buffer the zero borders of AP were last established for
     DevBuf staging_host;  // pinned host staging for image uploads / result downloads
+    bool guard = false;   // debug: new device allocations get canary bands on both sides and a poisoned interior (sva_debug_set_guard)
+    void device_bufs(std::vector<DevBuf*>& out);
+    void release(DevBuf& b);
 
     // ---- per-kernel timing of the last run ----
     bool timing = false;

@@ -4,18 +4,49 @@
 
 #include "sva_common.cuh"
 
+// Debug guard bands (sva_debug_set_guard): compute-sanitizer is not always available on a GPU box, so the library can check itself.
+// A guarded allocation is [GUARD_BYTES canary][payload, poisoned][GUARD_BYTES canary]; sva_debug_check_guards counts canary bytes
+// that changed (an out-of-bounds write), and the poison makes a read of never-written memory show up as a parity failure instead of
+// passing on the zeros a fresh cudaMalloc usually returns.
+static constexpr size_t GUARD_BYTES = 256 << 10;
+static constexpr int GUARD_CANARY = 0xA5, GUARD_POISON = 0xCD;
+
+__global__ void k_guard_count(const uint8_t* __restrict__ p, size_t n, unsigned long long* bad) {
+    unsigned long long local = 0;
+    for (size_t i = blockIdx.x * (size_t)blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) local += p[i] != GUARD_CANARY;
+    if (local) atomicAdd(bad, local);
+}
+
+void sva_ctx::release(DevBuf& b) {
+    if (b.p) cudaFree(b.base ? b.base : b.p);
+    b.p = b.base = nullptr;
+    b.bytes = 0;
+}
+
+void sva_ctx::device_bufs(std::vector<DevBuf*>& out) {
+    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf,
+           &alt.pad_ref, &alt.pad_imgs, &alt.ref_img, &alt.other_imgs, &alt.lines, &alt.mask, &alt.disp, &alt.subpix};
+}
+
 int sva_ctx::reserve(DevBuf& b, size_t bytes) {
     if (b.bytes >= bytes && b.p) return SVA_OK;
     if (b.p) {
         cudaStreamSynchronize(stream);
-        cudaFree(b.p);
-        b.p = nullptr; b.bytes = 0;
+        release(b);
     }
     size_t want = (bytes + 255) & ~(size_t)255;
-    cudaError_t e = cudaMalloc(&b.p, want);
-    if (e != cudaSuccess) {
-        b.p = nullptr;
+    void* raw = nullptr;
+    cudaError_t e = cudaMalloc(&raw, want + (guard ? 2 * GUARD_BYTES : 0));
+    if (e != cudaSuccess)
         return fail(e == cudaErrorMemoryAllocation ? SVA_ERR_NOMEM : SVA_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    if (guard) {
+        cudaMemsetAsync(raw, GUARD_CANARY, want + 2 * GUARD_BYTES, stream);
+        cudaMemsetAsync((uint8_t*)raw + GUARD_BYTES, GUARD_POISON, want, stream);
+        b.base = raw;
+        b.p = (uint8_t*)raw + GUARD_BYTES;
+    } else {
+        b.base = nullptr;
+        b.p = raw;
     }
     b.bytes = want;
     return SVA_OK;
@@ -88,12 +119,9 @@ int sva_destroy(sva_ctx* c) {
     cudaStreamSynchronize(c->stream);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(c->d2h_stream); }
-    DevBuf* bufs[] = {&c->ref_img, &c->other_imgs, &c->lines, &c->mask, &c->A, &c->AP, &c->pad_imgs, &c->pad_ref, &c->C, &c->Craw, &c->S, &c->disp, &c->subpix, &c->other_d, &c->scratch, &c->scratch2, &c->pace_buf};
-    for (DevBuf* b : bufs)
-        if (b->p) cudaFree(b->p);
-    DevBuf* alts[] = {&c->alt.pad_ref, &c->alt.pad_imgs, &c->alt.ref_img, &c->alt.other_imgs, &c->alt.lines, &c->alt.mask, &c->alt.disp, &c->alt.subpix};
-    for (DevBuf* b : alts)
-        if (b->p) cudaFree(b->p);
+    std::vector<DevBuf*> bufs;
+    c->device_bufs(bufs);
+    for (DevBuf* b : bufs) c->release(*b);
     if (c->h2d_stream) {
         cudaStreamDestroy(c->h2d_stream); cudaStreamDestroy(c->d2h_stream); cudaEventDestroy(c->ev_mark);
         for (int i = 0; i < 2; i++) { cudaEventDestroy(c->ev_h2d[i]); cudaEventDestroy(c->ev_compute[i]); cudaEventDestroy(c->ev_done[i]); }
@@ -126,6 +154,38 @@ int sva_use_own_stream(sva_ctx* c) {
 int sva_synchronize(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
+    return SVA_OK;
+}
+
+int sva_debug_set_guard(sva_ctx* c, int on) {  // applies to allocations made from now on
+    if (!c) return SVA_ERR_BAD_ARG;
+    c->guard = on != 0;
+    return SVA_OK;
+}
+
+int sva_debug_check_guards(sva_ctx* c, int64_t* guarded_buffers, int64_t* bad_bytes) {
+    if (!c || !guarded_buffers || !bad_bytes) return c ? c->fail(SVA_ERR_BAD_ARG, "check_guards: null argument") : SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_CUDA_OK(c, cudaDeviceSynchronize());
+    unsigned long long* d_bad = nullptr;
+    SVA_CUDA_OK(c, cudaMalloc(&d_bad, sizeof *d_bad));
+    cudaMemsetAsync(d_bad, 0, sizeof *d_bad, c->stream);
+    std::vector<DevBuf*> bufs;
+    c->device_bufs(bufs);
+    int64_t n = 0;
+    for (DevBuf* b : bufs) {
+        if (!b->p || !b->base) continue;
+        n++;
+        k_guard_count<<<64, 256, 0, c->stream>>>((const uint8_t*)b->base, GUARD_BYTES, d_bad);
+        k_guard_count<<<64, 256, 0, c->stream>>>((const uint8_t*)b->p + b->bytes, GUARD_BYTES, d_bad);
+    }
+    unsigned long long bad = 0;
+    cudaError_t e = cudaMemcpyAsync(&bad, d_bad, sizeof bad, cudaMemcpyDeviceToHost, c->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+    cudaFree(d_bad);
+    SVA_CUDA_OK(c, e);
+    *guarded_buffers = n;
+    *bad_bytes = (int64_t)bad;
     return SVA_OK;
 }
 

@@ -97,6 +97,16 @@ class DepthContext:
         check(self._h, self._L.sva_kernel_launches(self._h, C.byref(n)))
         return n.value
 
+    def set_guard(self, on=True):
+        """debug: device buffers allocated from now on get canary bands and a poisoned payload (see check_guards)"""
+        check(self._h, self._L.sva_debug_set_guard(self._h, int(on)))
+
+    def check_guards(self):
+        """-> (guarded buffers, overwritten canary bytes); the second number must be 0"""
+        n, bad = C.c_int64(), C.c_int64()
+        check(self._h, self._L.sva_debug_check_guards(self._h, C.byref(n), C.byref(bad)))
+        return n.value, bad.value
+
     def _shape(self):
         p = self.params
         return (p.height, p.width, p.num_disp)
