@@ -84,8 +84,7 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
     if name.startswith("k_sgm_store"):
         return 4 * de
     if name == "k_sgm_red_multi":  # launches_per_step tells which variant ran; bytes are per launch
-        dirs = p.n_paths - 2 if os.environ.get("SVA_SGM_FUSED_FINAL", "0") == "1" else p.n_paths
-        return 6 * de * dirs / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
+        return 6 * de * p.n_paths / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
     if name in ("k_wta_march", "k_wta_tile"):
         return 2 * de + 6 * px
     if name == "k_wta_seg":

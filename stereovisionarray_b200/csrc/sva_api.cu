@@ -32,6 +32,8 @@ static int check_params(sva_ctx* c, const sva_params* p) {
     if (sva_sgm_regs_per_lane(p->num_disp) == 0) return c->fail(SVA_ERR_BAD_ARG, "unsupported num_disp");
     // exact u32 box sums: 4k^2 * 255 * n_pairs must fit
     if (4.0 * p->win_half * p->win_half * 255.0 * p->n_pairs > 4.0e9) return c->fail(SVA_ERR_BAD_ARG, "window sum overflows u32");
+    // the marches index the volumes with 32-bit element cursors
+    if ((double)p->width * p->height * p->num_disp >= 4294967296.0) return c->fail(SVA_ERR_BAD_ARG, "frame too large: width * height * num_disp must be below 2^32");
     return SVA_OK;
 }
 
@@ -99,13 +101,12 @@ int sva_frame_set_debug(sva_ctx* c, int32_t store_full_s, uint32_t sgm_dir_mask)
 static int prezero_s(sva_ctx* c) {
     const sva_params& p = c->prm;
     c->s_prezeroed = false;
-    if (p.n_paths == 0 || c->tune_sgm_fused_final || c->sgm_dir_mask_override || !c->tune_prezero) return SVA_OK;
+    if (p.n_paths == 0 || c->sgm_dir_mask_override || !c->tune_prezero) return SVA_OK;
     const size_t bytes = (size_t)p.width * p.height * p.num_disp * sizeof(uint16_t);
     SVA_TRY(c->reserve(c->S, bytes + 64));
     if (!c->aux_stream) {
         SVA_CUDA_OK(c, cudaStreamCreateWithFlags(&c->aux_stream, cudaStreamNonBlocking));
         SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
-        SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
     }
     if (!c->ev_zero) SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_zero, cudaEventDisableTiming));
     SVA_CUDA_OK(c, cudaEventRecord(c->ev_fork, c->stream));            // after the previous frame's last reader of S

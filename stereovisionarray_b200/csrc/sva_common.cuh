@@ -70,8 +70,8 @@ struct sva_ctx {
     int sm_count = 148;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
-    cudaStream_t aux_stream = nullptr;  // second stream for kernels that overlap with the main one (k_sgm.cu), forked / joined with the two events
-    cudaEvent_t ev_fork = nullptr, ev_join = nullptr, ev_zero = nullptr;
+    cudaStream_t aux_stream = nullptr;  // second stream: the S memset of the next SGM runs next to K1a / K1b (sva_api.cu)
+    cudaEvent_t ev_fork = nullptr, ev_zero = nullptr;
     bool s_prezeroed = false;  // S is being zeroed on aux_stream for the SGM of this whole-frame run (ev_zero marks the end)
     int tune_prezero = 1;      // SVA_PREZERO: overlap the S memset with K1a / K1b
     // ---- streaming pipeline (sva_stream_*) ----
@@ -88,25 +88,15 @@ struct sva_ctx {
     int pair_begin = 0, pair_end = 0;
     bool has_mask = false;
     bool debug_store_full_s = false;
-    int tune_sgm_pf = 8;          // SVA_SGM_PF: cp.async prefetch depth of the SGM passes (8 or 16)
-    int tune_sgm_concurrent = 1;  // SVA_SGM_CONCURRENT: run the RED-accumulating SGM directions in one launch
-    int tune_sgm_fused_final = 0; // SVA_SGM_FUSED_FINAL: last path + K3 in one march (variant A) instead of all-RED + WTA march
-    int tune_sgm_split = 2;       // SVA_SGM_SPLIT: 0 = one launch, 1 = two (down + right, up + left), 2 = three (down-sweeping, up-sweeping, horizontal; default), 3 = six row-sweeping + two horizontal
+    int tune_sgm_split = 1;       // SVA_SGM_SPLIT: 8 paths as three launches (down-sweeping, up-sweeping, horizontal; default) or, 0, as one
     int tune_sgm_pace = -1;       // SVA_SGM_PACE: keep all CTAs of a row-sweeping launch within pace_window rounds (of 9 rows) of each other.
                                   // -1 = automatic: on when one image row of C + S (W*D*4 bytes) is 768 KB or more.  The three directions of such a
                                   // launch share C and S lines in L2 only while their rows stay within the L2-resident window; unpaced drift is harmless
                                   // at c1 (0.66 MB per row: 0.277 ms unpaced, 0.283 paced) and costly at c4 (1.47 MB per row: 1.355 -> 0.925 ms paced).
     int tune_sgm_pace_window = 2; // SVA_SGM_PACE_WINDOW: rounds of 9 rows
-    int tune_sgm_cta_sync = 1;    // SVA_SGM_CTA_SYNC: named barrier among the row-sweeping warps of a CTA every 9 rows
-    int tune_sgm_balanced = 1;    // SVA_SGM_BALANCED: one wave of identical CTAs (k per SM) so all lines advance at the same rate
-    int tune_sgm_lean = 1;        // SVA_SGM_LEAN: specialised accumulate kernel (k_sgm_acc) instead of the general march
     int tune_sgm_diag_split = 1;  // SVA_SGM_DIAG_SPLIT: diagonal lines run the march that is split at the wrap events (no per-step wrap logic)
-    int tune_sgm_overlap = 0;     // SVA_SGM_OVERLAP (experiments, off): 1 = horizontal launch on a second stream next to the row-sweeping ones, 2 = up next to down.
-                                  // Measured on B200 at c1: no gain either way (1.53 ms per frame in all three) — the launches contend for the same issue slots / L2 REDs
-    int tune_sgm_lpl = 32;        // SVA_SGM_LPL: lanes per path line in the accumulate passes (32 = one line per warp, 16 / 8 = two / four)
     int tune_ad_gather = 0;       // SVA_AD_GATHER=1: force the line-image gather AD kernel (k_ad.cu) even where the image-space kernel applies
     int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)
-    int tune_wta_march = 0;       // SVA_WTA_MARCH: K3 as a warp-per-row march instead of the tile kernel
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;

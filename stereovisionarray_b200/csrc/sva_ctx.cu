@@ -93,17 +93,8 @@ int sva_create(int device, sva_ctx** out) {
     c->sm_count = prop.multiProcessorCount;
     if (cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking) != cudaSuccess) { delete c; return SVA_ERR_CUDA; }
     c->stream = c->own_stream;
-    if (const char* e = getenv("SVA_SGM_PF")) c->tune_sgm_pf = atoi(e);
-    if (const char* e = getenv("SVA_SGM_CONCURRENT")) c->tune_sgm_concurrent = atoi(e);
-    if (const char* e = getenv("SVA_SGM_FUSED_FINAL")) c->tune_sgm_fused_final = atoi(e);
-    if (const char* e = getenv("SVA_WTA_MARCH")) c->tune_wta_march = atoi(e);
-    if (const char* e = getenv("SVA_SGM_LEAN")) c->tune_sgm_lean = atoi(e);
     if (const char* e = getenv("SVA_SGM_SPLIT")) c->tune_sgm_split = atoi(e);
-    if (const char* e = getenv("SVA_SGM_BALANCED")) c->tune_sgm_balanced = atoi(e);
-    if (const char* e = getenv("SVA_SGM_CTA_SYNC")) c->tune_sgm_cta_sync = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
-    if (const char* e = getenv("SVA_SGM_LPL")) c->tune_sgm_lpl = atoi(e);
-    if (const char* e = getenv("SVA_SGM_OVERLAP")) c->tune_sgm_overlap = atoi(e);
     if (const char* e = getenv("SVA_PREZERO")) c->tune_prezero = atoi(e);
     if (const char* e = getenv("SVA_SGM_DIAG_SPLIT")) c->tune_sgm_diag_split = atoi(e);
     if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
@@ -128,7 +119,7 @@ int sva_destroy(sva_ctx* c) {
     }
     if (c->staging_host.p) cudaFreeHost(c->staging_host.p);
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
-    if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); cudaEventDestroy(c->ev_join); }
+    if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); }
     if (c->ev_zero) cudaEventDestroy(c->ev_zero);
     cudaStreamDestroy(c->own_stream);
     delete c;

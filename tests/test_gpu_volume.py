@@ -176,3 +176,18 @@ def test_bad_arguments_fail_loudly(ctx):
     p = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2)
     with pytest.raises(SvaError):
         ctx.upload(p, sc["ref"][:, :30], sc["others"])  # wrong size
+    # a volume the 32-bit element cursors cannot address is refused before anything is allocated
+    p = abi.make_params(65536, 32768, 8, [(-1, 0)], win_half=2)
+    with pytest.raises(SvaError, match="2\\^32"):
+        ctx.upload(p, sc["ref"], sc["others"])
+    for bad in (dict(n_paths=3), dict(win_half=0), dict(win_half=57), dict(lr_gx=2), dict(min_disp=-1)):
+        with pytest.raises(SvaError):
+            ctx.upload(abi.make_params(40, 32, 16, [(-1, 0)], **{**dict(win_half=2), **bad}), sc["ref"], sc["others"])
+    p = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2)
+    p.p1, p.p2 = 9, 8  # P2 < P1
+    with pytest.raises(SvaError):
+        ctx.upload(p, sc["ref"], sc["others"])
+    # a refused upload leaves the context as it was, and usable
+    p = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2, n_paths=4, lr_gx=-1)
+    disp, _ = ctx.depth_from_array(p, sc["ref"], sc["others"])
+    assert disp.shape == (32, 40)
