@@ -49,26 +49,44 @@ struct SgmParams {
 // EDGE_BIAS (every lane active): instead of replacing the missing d-1 / d+1 neighbour of the first / last disparity by
 // +inf with two selects per step, the lane adds a per-lane P1 whose edge half is 0x7FFF (p1_up, p1_dn): the neighbour slot then holds a
 // bounded real value (<= 8190), 8190 + 0x7FFF < 2^16 does not wrap and is larger than every real cost, so the minimum ignores it.
-template <int NR, bool EDGE_BIAS>
+// BL > 0 (NR = 4): the block layout of VecBlk4 on BL lanes — registers 0,1 hold disparities 4l..4l+3, registers 2,3 hold 4BL+4l..4BL+4l+3,
+// so each block has its own lane-edge neighbours (two rotations each way among the BL active lanes; disparities 4BL-1 | 4BL meet across
+// lanes BL-1 | 0).  The range ends use the biased P1 of EDGE_BIAS: every rotation source is an active lane, so the stand-in is bounded.
+template <int NR, bool EDGE_BIAS, int BL>
 __device__ __forceinline__ void sgm_step(uint32_t (&L)[NR], const uint32_t (&Cc)[NR], uint32_t& mm, uint32_t& mp2, uint32_t p1p1, uint32_t p2p2,
                                          bool first_lane, bool last_lane, uint32_t p1_up, uint32_t p1_dn) {
-    uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1);
-    uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
-    if (!EDGE_BIAS) {
-        if (first_lane) up = SGM_INF2;
-        if (last_lane) dn = SGM_INF2;
-        p1_up = p1p1; p1_dn = p1p1;
-    }
-    uint32_t sh[NR + 1];  // sh[j] = values at d-1 of register j; sh[j+1] = values at d+1 of register j
-    sh[0] = __byte_perm(up, L[0], 0x5432);
+    uint32_t dm[NR], dp[NR];  // values at d-1 / d+1 of register j
+    if (BL > 0) {
+        static_assert(BL == 0 || NR == 4, "block layout: 8 disparities per lane");
+        const int lane = threadIdx.x & 31;
+        const int prev = first_lane ? BL - 1 : lane - 1, next = last_lane ? 0 : lane + 1;  // (lanes beyond BL idle along; any source will do)
+        const uint32_t a = __shfl_sync(0xffffffffu, L[1], prev), b = __shfl_sync(0xffffffffu, L[NR - 1], prev);
+        const uint32_t c = __shfl_sync(0xffffffffu, L[0], next), d = __shfl_sync(0xffffffffu, L[NR - 2], next);
+        const uint32_t up1 = first_lane ? a : b, dn0 = last_lane ? d : c;  // lane 0's a / lane BL-1's d: the other block's edge cell
+        dm[0] = __byte_perm(a, L[0], 0x5432);  // lane 0: a stands in for the missing d-1 of disparity 0 (any real value: p1_up is biased)
+        dp[0] = dm[1] = __byte_perm(L[0], L[1], 0x5432);
+        dp[1] = __byte_perm(L[1], dn0, 0x5432);
+        dm[NR - 2] = __byte_perm(up1, L[NR - 2], 0x5432);
+        dp[NR - 2] = dm[NR - 1] = __byte_perm(L[NR - 2], L[NR - 1], 0x5432);
+        dp[NR - 1] = __byte_perm(L[NR - 1], d, 0x5432);  // lane BL-1: d stands in for the missing d+1 of the last disparity (p1_dn is biased)
+    } else {
+        uint32_t up = __shfl_up_sync(0xffffffffu, L[NR - 1], 1);
+        uint32_t dn = __shfl_down_sync(0xffffffffu, L[0], 1);
+        if (!EDGE_BIAS) {
+            if (first_lane) up = SGM_INF2;
+            if (last_lane) dn = SGM_INF2;
+            p1_up = p1p1; p1_dn = p1p1;
+        }
+        dm[0] = __byte_perm(up, L[0], 0x5432);
 #pragma unroll
-    for (int j = 1; j < NR; j++) sh[j] = __byte_perm(L[j - 1], L[j], 0x5432);
-    sh[NR] = __byte_perm(L[NR - 1], dn, 0x5432);
+        for (int j = 1; j < NR; j++) dp[j - 1] = dm[j] = __byte_perm(L[j - 1], L[j], 0x5432);
+        dp[NR - 1] = __byte_perm(L[NR - 1], dn, 0x5432);
+    }
     uint32_t mloc = 0xFFFFFFFFu;
 #pragma unroll
     for (int j = 0; j < NR; j++) {
-        uint32_t t = __viaddmin_u16x2(sh[j], j == 0 ? p1_up : p1p1, L[j]);
-        t = __viaddmin_u16x2(sh[j + 1], j == NR - 1 ? p1_dn : p1p1, t);
+        uint32_t t = __viaddmin_u16x2(dm[j], j == 0 ? p1_up : p1p1, L[j]);
+        t = __viaddmin_u16x2(dp[j], j == NR - 1 ? p1_dn : p1p1, t);
         t = __vminu2(t, mp2);
         L[j] = Cc[j] + t - mm;  // both halves: t >= mm, no borrow; C + t - mm <= 8190, no carry
         mloc = __vminu2(mloc, L[j]);
@@ -82,11 +100,12 @@ int sva_run_wta(sva_ctx* ctx, const uint16_t* vol);
 
 // ---- the accumulate march: specialised at compile time on DIAG (wrap / restart logic only for diagonals), FULL (all 32 lanes
 // active: no predicates) and STORE (plain store vs RED), running 32-bit element cursors instead of recomputed cell indices.
-template <int NR, int PF, bool FULL, bool DIAG, bool STORE>
+template <int NR, int PF, bool FULL, bool DIAG, bool STORE, int BL>
 __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t ring,
                                               const int bar_threads, volatile int* s_pace /* [0] rounds finished by this CTA, [1] rounds finished by every CTA */,
                                               const bool leader) {
-    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
+    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2, LANE_ELEMS = BL ? 4 : NV;
+    using V = typename VecSel<NR, BL>::type;
     const int W = q.W, H = q.H, D = q.D;
     const int len = dy == 0 ? W : H;
     const int x0 = dy == 0 ? (dx > 0 ? 0 : W - 1) : line, y0 = dy == 0 ? line : (dy > 0 ? 0 : H - 1);
@@ -94,11 +113,11 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     // a diagonal's wrap at the image edge is a countdown instead of two coordinate compares: the recurrence saturates the integer
     // ALU pipe, so every ALU instruction shaved off the cursor bookkeeping is time.
     const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
-    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lane * NV);
+    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lane * LANE_ELEMS);
     // the cost volume may be slice-major (a lane's cells never straddle a slice: c_ds % NV == 0): same walk, pixel stride c_ds
     const int cds = q.c_ds > 0 ? q.c_ds : D;
     const uint32_t dstep_c = (uint32_t)((dy * W + dx) * cds), wrapfix_c = (uint32_t)(-dx * W * cds);
-    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lane * NV) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lane * NV) % cds) : start;
+    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lane * LANE_ELEMS) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lane * LANE_ELEMS) % cds) : start;
     uint32_t ic = start_c, is = start;                // prefetch cursor (C), accumulate cursor (S)
     int cc = dx > 0 ? W - x0 : x0 + 1, cs = cc;       // steps until each cursor leaves the image sideways
     const bool active = FULL || lane < q.lanes;
@@ -113,7 +132,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
     };
 #pragma unroll
     for (int u = 0; u < PF; u++) {
-        if (u < len) { if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
+        if (u < len) { if (active) V::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
         cp_async_commit();
     }
     uint32_t L[NR];
@@ -126,16 +145,16 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
         uint32_t Cc[NR];
 #pragma unroll
         for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
-        if (active) Vec<NR>::lds(slot_addr, Cc);
-        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
+        if (active) V::lds(slot_addr, Cc);
+        if (refill) { if (active) V::cp_async(refill_addr, q.C + ic); adv(ic, cc, dstep_c, wrapfix_c); }
         cp_async_commit();
         if (DIAG && restart) {
 #pragma unroll
             for (int j = 0; j < NR; j++) L[j] = 0;
             mm = 0; mp2 = q.p2p2;
         }
-        sgm_step<NR, FULL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
-        if (active) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
+        sgm_step<NR, FULL, BL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
+        if (active) { if (STORE) V::store(q.S + is, L); else V::red(q.S + is, L); }
         restart = adv(is, cs, dstep, wrapfix);
     };
     int s0 = 0;
@@ -165,18 +184,19 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
 // bound by the integer pipe): whole ring rounds of NS steps run unrolled, the few steps around an event run one at a time.  The wrap
 // step is a per-line constant, i.e. warp-uniform here.  The CTA barrier / pacing rhythm (every NS steps, same step indices in every
 // warp) is kept, so the warps of a CTA still meet the same number of times.
-template <int NR, int PF, bool FULL, bool STORE>
+template <int NR, int PF, bool FULL, bool STORE, int BL>
 __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const int dx, const int dy, const int line, const int lane,
                                                      const uint32_t ring, const int bar_threads, volatile int* s_pace, const bool leader) {
-    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2;
+    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2, LANE_ELEMS = BL ? 4 : NV;
+    using V = typename VecSel<NR, BL>::type;
     const int W = q.W, H = q.H, D = q.D;
     const int len = H;
     const int x0 = line, y0 = dy > 0 ? 0 : H - 1;
     const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
-    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lane * NV);
+    const uint32_t start = (uint32_t)(((long long)y0 * W + x0) * D + lane * LANE_ELEMS);
     const int cds = q.c_ds > 0 ? q.c_ds : D;
     const uint32_t dstep_c = (uint32_t)((dy * W + dx) * cds), wrapfix_c = (uint32_t)(-dx * W * cds);
-    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lane * NV) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lane * NV) % cds) : start;
+    const uint32_t start_c = q.c_ds > 0 ? (uint32_t)((long long)((lane * LANE_ELEMS) / cds) * H * W * cds + ((long long)y0 * W + x0) * cds + (lane * LANE_ELEMS) % cds) : start;
     uint32_t ic = start_c, is = start;
     const bool active = FULL || lane < q.lanes;
     const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
@@ -187,7 +207,7 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
 #pragma unroll
     for (int u = 0; u < PF; u++) {
         if (u < len) {
-            if (active) Vec<NR>::cp_async(ring + u * STAGE, q.C + ic);
+            if (active) V::cp_async(ring + u * STAGE, q.C + ic);
             ic += dstep_c;
             if (++adv_c == wc) { ic += wrapfix_c; wc += W; }
         }
@@ -202,11 +222,11 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
         uint32_t Cc[NR];
 #pragma unroll
         for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
-        if (active) Vec<NR>::lds(slot_addr, Cc);
-        if (refill) { if (active) Vec<NR>::cp_async(refill_addr, q.C + ic); ic += dstep_c; }
+        if (active) V::lds(slot_addr, Cc);
+        if (refill) { if (active) V::cp_async(refill_addr, q.C + ic); ic += dstep_c; }
         cp_async_commit();
-        sgm_step<NR, FULL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
-        if (active) { if (STORE) Vec<NR>::store(q.S + is, L); else Vec<NR>::red(q.S + is, L); }
+        sgm_step<NR, FULL, BL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
+        if (active) { if (STORE) V::store(q.S + is, L); else V::red(q.S + is, L); }
         is += dstep;
     };
     int s = 0, slot = 0, round = 0;
@@ -247,7 +267,7 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
 }
 
 // 40 registers: 48 resident warps per SM (e.g. two 22-warp CTAs of a paced c4 launch) must fit the 64 K register file
-template <int NR, int PF, bool FULL, bool STORE>
+template <int NR, int PF, bool FULL, bool STORE, int BL>
 __global__ void __maxnreg__(40)
 k_sgm_acc(SgmParams q) {
     constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
@@ -287,7 +307,7 @@ k_sgm_acc(SgmParams q) {
     const int dx = q.dxs[dir], dy = q.dys[dir];
     const int nlines = dy == 0 ? q.H : q.W;
     if (line >= nlines) return;
-    const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (4 * NR);
+    const uint32_t ring = smem_u32(smem_raw) + warp * RING_BYTES + lane * (BL ? 8 : 4 * NR);
     int bar_threads = 0;
     bool leader = false;
     if (q.balanced && dy != 0) {  // threads of this CTA that march down/up the rows (all do the same number of rounds)
@@ -298,12 +318,12 @@ k_sgm_acc(SgmParams q) {
     }
     volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
     if (dx != 0 && dy != 0) {
-        if (q.diag_split) sgm_acc_march_diag32<NR, PF, FULL, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
-        else sgm_acc_march<NR, PF, FULL, true, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
-    } else sgm_acc_march<NR, PF, FULL, false, STORE>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
+        if (q.diag_split) sgm_acc_march_diag32<NR, PF, FULL, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
+        else sgm_acc_march<NR, PF, FULL, true, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
+    } else sgm_acc_march<NR, PF, FULL, false, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
 }
 
-template <int NR, int PF, bool FULL, bool STORE>
+template <int NR, int PF, bool FULL, bool STORE, int BL>
 static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     constexpr size_t RING_BYTES = (size_t)(PF + 1) * 32 * 2 * NR * 2;  // per warp
     constexpr int FALLBACK_WARPS = 8;
@@ -321,7 +341,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
         if (w <= 32 && (size_t)w * RING_BYTES * m <= 200 * 1024 && w * 32 * m <= 2048) { warps = w; grid = g; qq.balanced = 1; break; }
     }
     const size_t smem = (size_t)warps * RING_BYTES;
-    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     qq.march_warps = warps;
     qq.pace_arrive = nullptr;
     int threads = warps * 32;
@@ -331,7 +351,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     if (qq.balanced && pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
         // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
         int per_sm = 0;
-        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE>, threads + 32, smem));
+        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, BL>, threads + 32, smem));
         if (getenv("SVA_DEBUG")) fprintf(stderr, "[sva] sgm_acc NR=%d ndirs=%d grid=%d threads=%d smem=%zu per_sm=%d\n", NR, q.ndirs, grid, threads + 32, smem, per_sm);
         if ((long long)per_sm * ctx->sm_count >= grid) {
             const int rounds = (q.H - PF) / (PF + 1);
@@ -351,7 +371,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     if (qq.pace_arrive && ctx->tune_sgm_diag_split < 2) qq.diag_split = 0;
     {
         LaunchScope ls(ctx, name);
-        k_sgm_acc<NR, PF, FULL, STORE><<<grid, threads, smem, ctx->stream>>>(qq);
+        k_sgm_acc<NR, PF, FULL, STORE, BL><<<grid, threads, smem, ctx->stream>>>(qq);
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     return SVA_OK;
@@ -363,8 +383,14 @@ static int launch_dirs_nr(sva_ctx* ctx, const SgmParams& q, bool store) {
     const bool full = q.lanes == 32;
     const char* nm = store ? (q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d"))
                            : (q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d")));
-    if (store) return full ? launch_acc<NR, SGM_PF, true, true>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, true>(ctx, q, nm);
-    return full ? launch_acc<NR, SGM_PF, true, false>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, false>(ctx, q, nm);
+    if constexpr (NR == 4) {  // D = 256 / 192 on a contiguous volume: the block layout (whole-sector copies and REDs)
+        if (q.c_ds == 0 && !getenv("SVA_SGM_NO_BLK")) {
+            if (q.lanes == 32) return store ? launch_acc<NR, SGM_PF, true, true, 32>(ctx, q, nm) : launch_acc<NR, SGM_PF, true, false, 32>(ctx, q, nm);
+            if (q.lanes == 24) return store ? launch_acc<NR, SGM_PF, false, true, 24>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, false, 24>(ctx, q, nm);
+        }
+    }
+    if (store) return full ? launch_acc<NR, SGM_PF, true, true, 0>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, true, 0>(ctx, q, nm);
+    return full ? launch_acc<NR, SGM_PF, true, false, 0>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, false, 0>(ctx, q, nm);
 }
 
 static int launch_dirs(sva_ctx* ctx, const SgmParams& q, int nr, bool store) {

@@ -91,3 +91,30 @@ template <> struct Vec<8> {
     }
 };
 
+// "Block" layout for 8 disparities per lane on BL lanes (D = 8 BL: 256 on a full warp, 192 on 24 lanes): lane l owns the 8-byte pairs
+// l and BL + l of the 2 BL pairs of a cell, i.e. disparities 4l..4l+3 and 4BL+4l..4BL+4l+3.  Every copy / load / RED instruction then
+// covers 8 BL contiguous bytes (whole sectors); in the plain layout (16 contiguous bytes per lane) each of the two 64-bit REDs of a lane
+// touches half of every sector of the cell, which is what bounded the D > 128 marches (B200: 0.71 -> 0.46 ms per row-sweeping launch at
+// 1280x960x256).  p points at the lane's first pair; the ring slot is 8 bytes per lane, the second block 8 BL bytes further.
+template <int BL> struct VecBlk4 {
+    static __device__ __forceinline__ void cp_async(uint32_t dst, const uint16_t* p) {
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst), "l"(p) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(dst + 8 * BL), "l"(p + 4 * BL) : "memory");
+    }
+    static __device__ __forceinline__ void lds(uint32_t src, uint32_t (&r)[4]) {
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(src));
+        asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(r[2]), "=r"(r[3]) : "r"(src + 8 * BL));
+    }
+    static __device__ __forceinline__ void store(uint16_t* p, const uint32_t (&r)[4]) {
+        *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]);
+        *reinterpret_cast<uint2*>(p + 4 * BL) = make_uint2(r[2], r[3]);
+    }
+    static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[4]) {
+        unsigned long long v0 = ((unsigned long long)r[1] << 32) | r[0], v1 = ((unsigned long long)r[3] << 32) | r[2];
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v0) : "memory");
+        asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p + 4 * BL), "l"(v1) : "memory");
+    }
+};
+
+template <int NR, int BL> struct VecSel { using type = VecBlk4<BL>; };
+template <int NR> struct VecSel<NR, 0> { using type = Vec<NR>; };
