@@ -280,7 +280,7 @@ def run_pair_sharded(args, rank, local_rank, world):
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
     b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
-    slices = args.c3_scheme == "slices"
+    slices = args.c3_scheme == "slices" and world > 1  # one GPU: nothing to exchange, the frame runs as one plain pipeline
     keep = {}
     if slices:
         ctx.upload(sdist.slice_params(p, rank, world), sc["ref"], sc["others"], sc["mask"])
@@ -338,7 +338,8 @@ def run_pair_sharded(args, rank, local_rank, world):
                           "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths,
                           "partitioning": ("disparity slices of %d (cost volume, no reduction) -> all-gather -> path directions %s -> reduce-scatter by row blocks -> "
                                            "row-sharded WTA; %d ranks" % (p.num_disp // world, sdist.direction_masks(p.n_paths, world), world)) if slices else
-                                          "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9),
+                                          ("single GPU: the whole frame, no exchange" if world == 1 else
+                                           "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9)),
                           "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
                "e2e": None, "gpu_launches": int(launches), "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "note": "see the c1 line for per-kernel rooflines"},
                "cpu_baseline": None, "clocks": clocks}

@@ -27,6 +27,9 @@
 #include "sva_vec.cuh"
 
 #define SGM_INF2 0x7FFF7FFFu
+constexpr size_t SGM_SMEM_PER_SM = 218 * 1024;  // ring space a resident wave may use per SM (228 KB minus the per-CTA reserve and the statics)
+constexpr int SGM_WARPS_PER_SM = 46;            // marching warps per SM at 40 registers: two CTAs of 23 + 1 helper warp (warps are allocated in fours:
+                                                // 2 x 24 x 32 x 40 registers fit the 64 K file, 2 x 28 do not)
 constexpr int SGM_PF = 8;  // steps of prefetch in flight per warp; the ring has PF + 1 stages (the slot refilled at step s was last read at step s-1)
 
 struct SgmParams {
@@ -43,6 +46,8 @@ struct SgmParams {
     int diag_split;     // diagonals run the event-split march (SVA_SGM_DIAG_SPLIT, default on)
     int c_ds;           // 0: C is [H][W][D]; > 0: C is slice-major [D / c_ds][H][W][c_ds] (disparity slices gathered from several GPUs)
     int balanced;       // grid = m * SM count; warp w of CTA b handles direction w % ndirs, line b + grid * (w / ndirs)
+    int ranged;         // 1: direction i contributes only its lines [line_lo[i], line_lo[i] + line_cnt[i]); warp w of CTA b takes the
+    int line_lo[8], line_cnt[8];  //    (b + grid * w)-th line of the concatenated ranges (a launch cut to what is resident at once)
 };
 
 // one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
@@ -266,6 +271,15 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
     if (s_pace && leader && lane == 0) s_pace[0] = round;  // all paced rounds done (lets the helper warp finish)
 }
 
+// g-th line of the concatenated per-direction ranges of a ranged launch
+__device__ __forceinline__ bool sgm_ranged_line(const SgmParams& q, int g, int& dir, int& line) {
+    for (int i = 0; i < q.ndirs; i++) {
+        if (g < q.line_cnt[i]) { dir = i; line = q.line_lo[i] + g; return true; }
+        g -= q.line_cnt[i];
+    }
+    return false;
+}
+
 // 40 registers: 48 resident warps per SM (e.g. two 22-warp CTAs of a paced c4 launch) must fit the 64 K register file
 template <int NR, int PF, bool FULL, bool STORE, int BL>
 __global__ void __maxnreg__(40)
@@ -297,8 +311,10 @@ k_sgm_acc(SgmParams q) {
             return;
         }
     }
-    int dir, line;
-    if (q.balanced) {  // every CTA carries the same mix of directions and every SM the same number of CTAs -> all lines advance at the same rate
+    int dir = 0, line = 0;
+    if (q.ranged) {
+        if (!sgm_ranged_line(q, q.balanced ? blockIdx.x + gridDim.x * warp : blockIdx.x * q.march_warps + warp, dir, line)) return;
+    } else if (q.balanced) {  // every CTA carries the same mix of directions and every SM the same number of CTAs -> all lines advance at the same rate
         dir = warp % q.ndirs;
         line = blockIdx.x + gridDim.x * (warp / q.ndirs);
     } else {
@@ -312,8 +328,14 @@ k_sgm_acc(SgmParams q) {
     bool leader = false;
     if (q.balanced && dy != 0) {  // threads of this CTA that march down/up the rows (all do the same number of rounds)
         int first = -1;
-        for (int w = 0; w < q.march_warps; w++)
-            if (q.dys[w % q.ndirs] != 0 && (int)(blockIdx.x + gridDim.x * (w / q.ndirs)) < q.W) { bar_threads += 32; if (first < 0) first = w; }
+        for (int w = 0; w < q.march_warps; w++) {
+            bool marches;
+            if (q.ranged) {
+                int d_ = 0, l_ = 0;
+                marches = sgm_ranged_line(q, blockIdx.x + gridDim.x * w, d_, l_) && q.dys[d_] != 0;
+            } else marches = q.dys[w % q.ndirs] != 0 && (int)(blockIdx.x + gridDim.x * (w / q.ndirs)) < q.W;
+            if (marches) { bar_threads += 32; if (first < 0) first = w; }
+        }
         leader = warp == first;
     }
     volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
@@ -335,13 +357,19 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     qq.diag_split = ctx->tune_sgm_diag_split;
     // one wave of identical CTAs: m CTAs per SM, as few warps per CTA as cover all lines (every CTA the same mix of directions, every SM
     // the same number of CTAs, so all lines advance at the same rate); launches too large for one wave fall back to 8-warp CTAs
+    int total = 0;
+    for (int i = 0; i < q.ndirs; i++) total += q.line_cnt[i];
     for (int m = 1; m <= 8; m++) {
         const int g = ctx->sm_count * m;
-        const int w = div_up(nlines, g) * q.ndirs;  // lines per direction per CTA x directions
-        if (w <= 32 && (size_t)w * RING_BYTES * m <= 200 * 1024 && w * 32 * m <= 2048) { warps = w; grid = g; qq.balanced = 1; break; }
+        const int w = q.ranged ? div_up(total, g) : div_up(nlines, g) * q.ndirs;  // lines per direction per CTA x directions
+        const size_t smem_cap = q.ranged ? SGM_SMEM_PER_SM : 200 * 1024;
+        const int wmax = q.ranged ? 31 : 32;  // a ranged launch is always paced: leave room for the helper warp
+        if (w <= wmax && (size_t)w * RING_BYTES * m <= smem_cap && w * 32 * m <= 2048) { warps = w; grid = g; qq.balanced = 1; break; }
     }
+    if (q.ranged && !qq.balanced) grid = div_up(total, FALLBACK_WARPS);
     const size_t smem = (size_t)warps * RING_BYTES;
     SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     qq.march_warps = warps;
     qq.pace_arrive = nullptr;
     int threads = warps * 32;
@@ -414,6 +442,32 @@ static const int DIRS[8][2] = {{0, 1}, {0, -1}, {1, 0}, {-1, 0}, {1, 1}, {-1, 1}
 static void set_dirs(SgmParams& q, const int* idx, int n) {
     q.ndirs = n;
     for (int i = 0; i < n; i++) { q.dxs[i] = DIRS[idx[i]][0]; q.dys[i] = DIRS[idx[i]][1]; }
+}
+
+// One group of directions that sweep the rows the same way.  They share a row's C and S lines in L2 only while ALL their lines are
+// resident and paced; a group with more lines than fit one resident wave (3 x 3840 at c3) is therefore cut into launches that do fit —
+// whole directions first, one direction split by line range — instead of running in unsynchronised waves that share nothing.
+static int launch_row_group(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, int n) {
+    set_dirs(q, idx, n);
+    q.ranged = 0;
+    const size_t ring = (size_t)(SGM_PF + 1) * 32 * 2 * nr * 2;
+    const int cap = ctx->sm_count * std::min(SGM_WARPS_PER_SM, (int)(SGM_SMEM_PER_SM / ring));
+    const bool pace = ctx->tune_sgm_pace < 0 ? (size_t)q.W * q.D * 4 >= 768 * 1024 : ctx->tune_sgm_pace != 0;
+    if (!pace || n * q.W <= cap || q.W > cap || getenv("SVA_SGM_NO_RANGED")) return launch_dirs(ctx, q, nr, false);
+    const int launches = div_up(n * q.W, cap), per_launch = div_up(n * q.W, launches);  // equal shares: every launch streams the whole volume once
+    int dir = 0, lo = 0;
+    while (dir < n) {
+        SgmParams s = q;
+        s.ranged = 1; s.ndirs = 0;
+        for (int room = per_launch; dir < n && room > 0;) {
+            const int take = std::min(room, q.W - lo);
+            s.dxs[s.ndirs] = q.dxs[dir]; s.dys[s.ndirs] = q.dys[dir]; s.line_lo[s.ndirs] = lo; s.line_cnt[s.ndirs] = take; s.ndirs++;
+            room -= take; lo += take;
+            if (lo == q.W) { dir++; lo = 0; }
+        }
+        SVA_TRY(launch_dirs(ctx, s, nr, false));
+    }
+    return SVA_OK;
 }
 
 // exactly the directions of dir_mask, one launch each: the first stores, the others RED, so S ends up as their sum
@@ -489,10 +543,10 @@ int sva_run_sgm(sva_ctx* ctx) {
         // row's C and S lines while these are in L2.  The horizontal lines (W steps each, every row in flight at once) cannot share
         // and get their own launch.
         static const int grp[3][3] = {{0, 4, 5}, {1, 6, 7}, {2, 3, -1}};
-        for (int g = 0; g < 3; g++) {
-            set_dirs(q, grp[g], g == 2 ? 2 : 3);
-            SVA_TRY(launch_dirs(ctx, q, nr, false));
-        }
+        SVA_TRY(launch_row_group(ctx, q, nr, grp[0], 3));
+        SVA_TRY(launch_row_group(ctx, q, nr, grp[1], 3));
+        set_dirs(q, grp[2], 2);
+        SVA_TRY(launch_dirs(ctx, q, nr, false));
     } else {  // 4 paths (or SVA_SGM_SPLIT=0): one launch, directions that sweep the same rows next to each other
         static const int all8[8] = {0, 4, 5, 1, 6, 7, 2, 3}, all4[4] = {0, 1, 2, 3};
         set_dirs(q, n == 8 ? all8 : all4, n);

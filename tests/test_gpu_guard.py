@@ -12,10 +12,13 @@ from test_gpu_volume import CASES, OFF8
 pytestmark = pytest.mark.gpu
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
-# two frames wide enough for many CTAs per launch: c1-like rows (unpaced SGM) and c2-like rows (W * D * 4 >= 768 KB: paced SGM)
+# frames wide enough for many CTAs per launch: c1-like rows (unpaced SGM) and c2-like rows (W * D * 4 >= 768 KB: paced SGM)
 WIDE = [
     (96, 1280, 128, OFF8, dict(win_half=20, n_paths=8, lr_gx=-1)),
     (80, 1024, 192, OFF8, dict(win_half=20, n_paths=8, lr_gx=-1)),
+    # c3-wide rows: three directions x 3840 lines exceed one resident wave, so each row-sweeping group runs as ranged launches
+    (48, 3840, 256, [(-1, 0), (1, 1)], dict(win_half=4, n_paths=8, lr_gx=-1)),
+    (40, 3840, 192, [(-1, 0), (0, -1)], dict(win_half=3, n_paths=8, lr_gx=1)),
 ]
 
 
