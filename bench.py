@@ -77,15 +77,15 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
     """per launch, DESIGN.md §4: s_C = s_S = 2 bytes"""
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
-    if name in ("k_ad_volume", "k_ad_planar", "k_ad_tile"):
+    if name in ("k_ad_planar", "k_ad_tile"):
         return n_cam * px + 2 * de
     if name in ("k_box_cost", "k_box_planar"):
         return 4 * de
     if name.startswith("k_sgm_store"):
         return 4 * de
-    if name == "k_sgm_red_multi":  # launches_per_step tells which variant ran; bytes are per launch
+    if name == "k_sgm_red_multi":  # bytes per launch: the frame's 6P - 4 ~ 6P bytes per cell spread over its launches
         return 6 * de * p.n_paths / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
-    if name in ("k_wta_march", "k_wta_tile"):
+    if name == "k_wta_tile":
         return 2 * de + 6 * px
     if name == "k_wta_seg":
         return 2 * de + 6 * px   # S once, winner map + the other view's key map
@@ -95,8 +95,6 @@ def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
         return 10 * px
     if name.startswith("k_sgm_red"):
         return 6 * de
-    if name == "k_sgm_final":
-        return 4 * de + 6 * px
     return None
 
 
