@@ -219,8 +219,17 @@ int sva_frame_set_params(sva_ctx* ctx, const sva_params* p);                    
 /* dir_mask bit i = direction i of {v+, v-, h+, h-, d++, d-+, d+-, d--}; slice_disp = D/G for a slice-major volume, 0 for [H][W][D] */
 int sva_frame_sgm_directions(sva_ctx* ctx, const void* cost_dev, int32_t slice_disp, uint32_t dir_mask, int32_t rows_alloc, void** out_s_ptr,
                              size_t* out_bytes);
-int sva_frame_wta_rows(sva_ctx* ctx, const void* s_rows_dev, int32_t y0, int32_t rows);  /* s_rows_dev = image rows [y0, y0+rows) of S */
+int sva_frame_wta_rows(sva_ctx* ctx, const void* s_rows_dev, int32_t y0, int32_t rows);  /* s_rows_dev = image rows [y0, y0+rows) of S (NULL: the ctx's own S) */
 int sva_frame_download_disparity_rows(sva_ctx* ctx, int32_t rows, uint16_t* out_disp, float* out_subpix);
+
+/* ---- building blocks for ONE frame sharded by ROW BLOCKS end to end: no volume ever crosses GPUs -------------------------
+ * Rank r owns image rows [y0, y0 + rows).  sva_frame_rows_begin zeroes those rows of the aggregation volume.  sva_frame_sgm_rows runs one
+ * direction group on the block: group 2 = {h+, h-} (local), group 0 = {v+, d++, d-+} sweeping down, group 1 = {v-, d+-, d--} sweeping up.
+ * A row-sweeping group continues the path lines of the block above (below): state_in / state_out are device buffers of 3 * W * D u16
+ * holding L of every line after the neighbouring block's last row / after this block's last row (NULL at the sweep's first / last block);
+ * the caller moves them between GPUs (a few MB per hop).  sva_frame_wta_rows(ctx, NULL, y0, rows) then runs K3 on the block. */
+int sva_frame_rows_begin(sva_ctx* ctx, int32_t y0, int32_t rows);
+int sva_frame_sgm_rows(sva_ctx* ctx, int32_t group, int32_t y0, int32_t rows, const void* state_in, void* state_out);
 
 #ifdef __cplusplus
 }

@@ -22,6 +22,7 @@ EXPORTS = [
     "sva_frame_download_ad", "sva_frame_download_cost", "sva_frame_download_raw_cost", "sva_frame_download_sgm",
     "sva_frame_download_disparity", "sva_frame_ad_device_ptr", "sva_frame_mark_ad_ready",
     "sva_frame_cost_device_ptr", "sva_frame_set_params", "sva_frame_sgm_directions", "sva_frame_wta_rows", "sva_frame_download_disparity_rows",
+    "sva_frame_rows_begin", "sva_frame_sgm_rows",
 ]
 
 _lib = None

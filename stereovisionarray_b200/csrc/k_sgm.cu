@@ -48,6 +48,12 @@ struct SgmParams {
     int balanced;       // grid = m * SM count; warp w of CTA b handles direction w % ndirs, line b + grid * (w / ndirs)
     int ranged;         // 1: direction i contributes only its lines [line_lo[i], line_lo[i] + line_cnt[i]); warp w of CTA b takes the
     int line_lo[8], line_cnt[8];  //    (b + grid * w)-th line of the concatenated ranges (a launch cut to what is resident at once)
+    // row-block pipeline across GPUs (sva_run_sgm_rows): a row-sweeping launch marches only image rows [row_y0, row_y0 + row_cnt) and
+    // hands the state of every path line — L after the block's last row — to the GPU that owns the next rows
+    int row_y0, row_cnt;
+    const uint16_t* state_in;   // [3][W][D] (slot, line, disparity in the lane layout of S); nullptr where the block starts the sweep
+    uint16_t* state_out;        // same shape; nullptr where the block ends the sweep
+    int state_slot[8];          // slot of direction i of this launch
 };
 
 // one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
@@ -271,6 +277,90 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
     if (s_pace && leader && lane == 0) s_pace[0] = round;  // all paced rounds done (lets the helper warp finish)
 }
 
+// Row-block march (dy != 0): the generic march over image rows [row_y0, row_y0 + row_cnt) only.  A line that was already under way
+// above (below) the block continues from the L its previous owner stored; its minimum is recomputed from that L.  A line whose
+// predecessor cell lies outside the image at the block's first row (the sweep's first row, or a diagonal that has just wrapped) starts
+// fresh exactly as in the whole-frame march.  Column of line x0 after t rows: (x0 + dx * t) mod W.
+template <int NR, int PF, bool FULL, bool STORE, int BL>
+__device__ __forceinline__ void sgm_rows_march(const SgmParams& q, const int dx, const int dy, const int slot, const int line, const int lane,
+                                               const uint32_t ring, const int bar_threads, volatile int* s_pace, const bool leader) {
+    constexpr int NS = PF + 1, NV = 2 * NR, STAGE = 32 * NV * 2, LANE_ELEMS = BL ? 4 : NV;
+    using V = typename VecSel<NR, BL>::type;
+    const int W = q.W, H = q.H, D = q.D;
+    const int len = q.row_cnt;
+    const int ya = dy > 0 ? q.row_y0 : q.row_y0 + q.row_cnt - 1;  // first row of the block in sweep order
+    const int t = dy > 0 ? ya : H - 1 - ya;                        // rows the line has already crossed
+    int xa = (int)(((long long)line + (long long)dx * t) % W);
+    if (xa < 0) xa += W;
+    const uint32_t dstep = (uint32_t)((dy * W + dx) * D), wrapfix = (uint32_t)(-dx * W * D);
+    const uint32_t start = (uint32_t)(((long long)ya * W + xa) * D + lane * LANE_ELEMS);
+    uint32_t ic = start, is = start;
+    int cc = dx > 0 ? W - xa : (dx < 0 ? xa + 1 : 0x7FFFFFFF), cs = cc;  // steps until each cursor leaves the image sideways
+    const bool active = FULL || lane < q.lanes;
+    const bool first_lane = lane == 0, last_lane = FULL ? lane == 31 : lane == q.lanes - 1;
+    const uint32_t p1_up = first_lane ? (q.p1p1 & 0xFFFF0000u) | 0x7FFFu : q.p1p1, p1_dn = last_lane ? (q.p1p1 & 0x0000FFFFu) | 0x7FFF0000u : q.p1p1;
+    auto adv = [&](uint32_t& i, int& cnt) -> bool {
+        i += dstep;
+        if (--cnt == 0) { cnt = W; i += wrapfix; return true; }
+        return false;
+    };
+#pragma unroll
+    for (int u = 0; u < PF; u++) {
+        if (u < len) { if (active) V::cp_async(ring + u * STAGE, q.C + ic); adv(ic, cc); }
+        cp_async_commit();
+    }
+    const size_t state_at = ((size_t)slot * W + line) * D + lane * LANE_ELEMS;
+    const bool fresh = t == 0 || (dx > 0 && xa == 0) || (dx < 0 && xa == W - 1) || q.state_in == nullptr;
+    uint32_t L[NR];
+    uint32_t mm = 0, mp2 = q.p2p2;
+#pragma unroll
+    for (int j = 0; j < NR; j++) L[j] = 0;
+    if (!fresh) {  // warp-uniform: t, xa and the pointer are per line
+#pragma unroll
+        for (int j = 0; j < NR; j++) L[j] = SGM_INF2;
+        if (active) V::load(q.state_in + state_at, L);
+        uint32_t mloc = L[0];
+#pragma unroll
+        for (int j = 1; j < NR; j++) mloc = __vminu2(mloc, L[j]);
+        mm = __reduce_min_sync(0xffffffffu, min(mloc & 0xFFFFu, mloc >> 16)) * 0x10001u;
+        mp2 = mm + q.p2p2;
+    }
+    bool restart = false;
+    auto step = [&](const uint32_t slot_addr, const uint32_t refill_addr, const bool refill) {
+        cp_async_wait<PF - 1>();
+        uint32_t Cc[NR];
+#pragma unroll
+        for (int j = 0; j < NR; j++) Cc[j] = SGM_INF2;
+        if (active) V::lds(slot_addr, Cc);
+        if (refill) { if (active) V::cp_async(refill_addr, q.C + ic); adv(ic, cc); }
+        cp_async_commit();
+        if (restart) {
+#pragma unroll
+            for (int j = 0; j < NR; j++) L[j] = 0;
+            mm = 0; mp2 = q.p2p2;
+        }
+        sgm_step<NR, FULL, BL>(L, Cc, mm, mp2, q.p1p1, q.p2p2, first_lane, last_lane, p1_up, p1_dn);
+        if (active) { if (STORE) V::store(q.S + is, L); else V::red(q.S + is, L); }
+        restart = adv(is, cs);
+    };
+    int s0 = 0;
+    for (; s0 + NS + PF <= len; s0 += NS) {
+        if (bar_threads) {  // same CTA rhythm and global pacing as the whole-frame march
+            asm volatile("bar.sync 1, %0;" ::"r"(bar_threads) : "memory");
+            if (s_pace) {
+                const int round = s0 / NS;
+                if (leader && lane == 0) s_pace[0] = round;
+                for (int spin = 0; spin < 4096 && round > s_pace[1] + q.pace_window; spin++) __nanosleep(128);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < NS; u++) step(ring + u * STAGE, ring + ((u + PF) % NS) * STAGE, true);
+    }
+    if (s_pace && leader && lane == 0) s_pace[0] = s0 / NS;
+    for (int s = s0; s < len; s++) step(ring + (s % NS) * STAGE, ring + ((s + PF) % NS) * STAGE, s + PF < len);
+    if (q.state_out && active) V::store(q.state_out + state_at, L);
+}
+
 // g-th line of the concatenated per-direction ranges of a ranged launch
 __device__ __forceinline__ bool sgm_ranged_line(const SgmParams& q, int g, int& dir, int& line) {
     for (int i = 0; i < q.ndirs; i++) {
@@ -281,7 +371,7 @@ __device__ __forceinline__ bool sgm_ranged_line(const SgmParams& q, int g, int& 
 }
 
 // 40 registers: 48 resident warps per SM (e.g. two 22-warp CTAs of a paced c4 launch) must fit the 64 K register file
-template <int NR, int PF, bool FULL, bool STORE, int BL>
+template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS>
 __global__ void __maxnreg__(40)
 k_sgm_acc(SgmParams q) {
     constexpr int RING_BYTES = (PF + 1) * 32 * 2 * NR * 2;
@@ -339,13 +429,17 @@ k_sgm_acc(SgmParams q) {
         leader = warp == first;
     }
     volatile int* pace = (q.pace_arrive && bar_threads) ? s_pace : nullptr;
+    if (ROWS) {  // row-sweeping directions only (the host never puts a horizontal one into a ROWS launch)
+        sgm_rows_march<NR, PF, FULL, STORE, BL>(q, dx, dy, q.state_slot[dir], line, lane, ring, bar_threads, pace, leader);
+        return;
+    }
     if (dx != 0 && dy != 0) {
         if (q.diag_split) sgm_acc_march_diag32<NR, PF, FULL, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
         else sgm_acc_march<NR, PF, FULL, true, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
     } else sgm_acc_march<NR, PF, FULL, false, STORE, BL>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
 }
 
-template <int NR, int PF, bool FULL, bool STORE, int BL>
+template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS = false>
 static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     constexpr size_t RING_BYTES = (size_t)(PF + 1) * 32 * 2 * NR * 2;  // per warp
     constexpr int FALLBACK_WARPS = 8;
@@ -368,8 +462,8 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     }
     if (q.ranged && !qq.balanced) grid = div_up(total, FALLBACK_WARPS);
     const size_t smem = (size_t)warps * RING_BYTES;
-    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL, ROWS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_sgm_acc<NR, PF, FULL, STORE, BL, ROWS>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     qq.march_warps = warps;
     qq.pace_arrive = nullptr;
     int threads = warps * 32;
@@ -379,10 +473,10 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     if (qq.balanced && pace && q.ndirs > 1 && n_vert && q.W >= grid && warps < 32) {
         // global pacing needs every CTA resident (the grid is one balanced wave by construction; check the occupancy anyway)
         int per_sm = 0;
-        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, BL>, threads + 32, smem));
+        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sgm_acc<NR, PF, FULL, STORE, BL, ROWS>, threads + 32, smem));
         if (getenv("SVA_DEBUG")) fprintf(stderr, "[sva] sgm_acc NR=%d ndirs=%d grid=%d threads=%d smem=%zu per_sm=%d\n", NR, q.ndirs, grid, threads + 32, smem, per_sm);
         if ((long long)per_sm * ctx->sm_count >= grid) {
-            const int rounds = (q.H - PF) / (PF + 1);
+            const int rounds = ((ROWS ? q.row_cnt : q.H) - PF) / (PF + 1);
             if (rounds > ctx->tune_sgm_pace_window) {
                 SVA_TRY(ctx->reserve(ctx->pace_buf, ((size_t)rounds + 16) * sizeof(unsigned int)));
                 SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->pace_buf.p, 0, ((size_t)rounds + 16) * sizeof(unsigned int), ctx->stream));
@@ -399,7 +493,7 @@ static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
     if (qq.pace_arrive && ctx->tune_sgm_diag_split < 2) qq.diag_split = 0;
     {
         LaunchScope ls(ctx, name);
-        k_sgm_acc<NR, PF, FULL, STORE, BL><<<grid, threads, smem, ctx->stream>>>(qq);
+        k_sgm_acc<NR, PF, FULL, STORE, BL, ROWS><<<grid, threads, smem, ctx->stream>>>(qq);
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     return SVA_OK;
@@ -411,6 +505,14 @@ static int launch_dirs_nr(sva_ctx* ctx, const SgmParams& q, bool store) {
     const bool full = q.lanes == 32;
     const char* nm = store ? (q.dys[0] == 0 ? "k_sgm_store_h" : (q.dxs[0] == 0 ? "k_sgm_store_v" : "k_sgm_store_d"))
                            : (q.ndirs > 1 ? "k_sgm_red_multi" : (q.dys[0] == 0 ? "k_sgm_red_h" : (q.dxs[0] == 0 ? "k_sgm_red_v" : "k_sgm_red_d")));
+    if (q.row_cnt > 0 && q.dys[0] != 0) {  // a row block of a row-sweeping group (REDs only, contiguous volume)
+        if (store || q.c_ds != 0) return ctx->fail(SVA_ERR_BAD_ARG, "internal: row-block launches accumulate into a contiguous volume");
+        if constexpr (NR == 4) {
+            if (q.lanes == 32) return launch_acc<NR, SGM_PF, true, false, 32, true>(ctx, q, nm);
+            if (q.lanes == 24) return launch_acc<NR, SGM_PF, false, false, 24, true>(ctx, q, nm);
+        }
+        return full ? launch_acc<NR, SGM_PF, true, false, 0, true>(ctx, q, nm) : launch_acc<NR, SGM_PF, false, false, 0, true>(ctx, q, nm);
+    }
     if constexpr (NR == 4) {  // D = 256 / 192 on a contiguous volume: the block layout (whole-sector copies and REDs)
         if (q.c_ds == 0 && !getenv("SVA_SGM_NO_BLK")) {
             if (q.lanes == 32) return store ? launch_acc<NR, SGM_PF, true, true, 32>(ctx, q, nm) : launch_acc<NR, SGM_PF, true, false, 32>(ctx, q, nm);
@@ -461,7 +563,8 @@ static int launch_row_group(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, 
         s.ranged = 1; s.ndirs = 0;
         for (int room = per_launch; dir < n && room > 0;) {
             const int take = std::min(room, q.W - lo);
-            s.dxs[s.ndirs] = q.dxs[dir]; s.dys[s.ndirs] = q.dys[dir]; s.line_lo[s.ndirs] = lo; s.line_cnt[s.ndirs] = take; s.ndirs++;
+            s.dxs[s.ndirs] = q.dxs[dir]; s.dys[s.ndirs] = q.dys[dir]; s.state_slot[s.ndirs] = q.state_slot[dir];
+            s.line_lo[s.ndirs] = lo; s.line_cnt[s.ndirs] = take; s.ndirs++;
             room -= take; lo += take;
             if (lo == q.W) { dir++; lo = 0; }
         }
@@ -511,6 +614,35 @@ int sva_run_sgm_dirs(sva_ctx* ctx, const uint16_t* Cext, int c_ds, uint32_t dir_
     SVA_TRY(run_dir_mask(ctx, q, nr, dir_mask & 0xFFu));
     ctx->have_sgm = true;
     return SVA_OK;
+}
+
+// One direction group of the frame on image rows [y0, y0 + rows) only, accumulated (RED) into those rows of ctx->S, which the caller has
+// zeroed: group 0 = {v+, d++, d-+} (sweeps down), 1 = {v-, d+-, d--} (sweeps up), 2 = {h+, h-}.  state_in / state_out: [3][W][D] u16 device
+// buffers carrying L of every path line across the block boundary (nullptr at the sweep's first / last block); unused for group 2.
+int sva_run_sgm_rows(sva_ctx* ctx, int group, int y0, int rows, const uint16_t* state_in, uint16_t* state_out) {
+    const sva_params& p = ctx->prm;
+    const int W = p.width, H = p.height, D = p.num_disp;
+    const int nr = sva_sgm_regs_per_lane(D);
+    if (nr == 0) return ctx->fail(SVA_ERR_BAD_ARG, "unsupported num_disp");
+    if (group < 0 || group > 2 || y0 < 0 || rows < 1 || y0 + rows > H) return ctx->fail(SVA_ERR_BAD_ARG, "sgm_rows: bad group or row block");
+    if (p.n_paths != 8) return ctx->fail(SVA_ERR_BAD_ARG, "sgm_rows: 8 paths only");
+    if (!ctx->S.p || ctx->S.bytes < (size_t)W * H * D * sizeof(uint16_t)) return ctx->fail(SVA_ERR_STATE, "sgm_rows: no aggregation volume (sva_frame_rows_begin first)");
+    SgmParams q{};
+    fill_params(ctx, q, ctx->C.as<uint16_t>(), 0);
+    static const int grp[3][3] = {{0, 4, 5}, {1, 6, 7}, {2, 3, -1}};
+    if (group == 2) {  // the rows are the lines: a ranged launch of the ordinary march
+        set_dirs(q, grp[2], 2);
+        q.ranged = 1;
+        for (int i = 0; i < 2; i++) { q.line_lo[i] = y0; q.line_cnt[i] = rows; }
+        return launch_dirs(ctx, q, nr, false);
+    }
+    const bool first_block = group == 0 ? y0 == 0 : y0 + rows == H, last_block = group == 0 ? y0 + rows == H : y0 == 0;
+    if (!first_block && !state_in) return ctx->fail(SVA_ERR_BAD_ARG, "sgm_rows: this block continues a sweep and needs state_in");
+    q.row_y0 = y0; q.row_cnt = rows;
+    q.state_in = first_block ? nullptr : state_in;
+    q.state_out = last_block ? nullptr : state_out;
+    for (int i = 0; i < 3; i++) q.state_slot[i] = i;
+    return launch_row_group(ctx, q, nr, grp[group], 3);
 }
 
 int sva_run_sgm(sva_ctx* ctx) {

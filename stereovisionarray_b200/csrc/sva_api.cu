@@ -16,6 +16,7 @@ uint8_t* sva_ad2_view_origin(sva_ctx* ctx, int k);
 int sva_run_ad2(sva_ctx* ctx);
 int sva_run_sgm_dirs(sva_ctx* ctx, const uint16_t* Cext, int c_ds, uint32_t dir_mask, int rows_alloc);
 int sva_run_wta_rows(sva_ctx* ctx, const uint16_t* vol, int y0, int rows);
+int sva_run_sgm_rows(sva_ctx* ctx, int group, int y0, int rows, const uint16_t* state_in, uint16_t* state_out);
 int sva_ap_unpack(sva_ctx* ctx);
 
 static int check_params(sva_ctx* c, const sva_params* p) {
@@ -320,10 +321,37 @@ int sva_frame_sgm_directions(sva_ctx* c, const void* cost_dev, int32_t slice_dis
     return SVA_OK;
 }
 
+int sva_frame_rows_begin(sva_ctx* c, int32_t y0, int32_t rows) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
+    const sva_params& p = c->prm;
+    if (y0 < 0 || rows < 1 || y0 + rows > p.height) return c->fail(SVA_ERR_BAD_ARG, "rows_begin: bad row block");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    const size_t row_bytes = (size_t)p.width * p.num_disp * sizeof(uint16_t);
+    SVA_TRY(c->reserve(c->S, row_bytes * p.height + 64));
+    SVA_CUDA_OK(c, cudaMemsetAsync((uint8_t*)c->S.p + row_bytes * y0, 0, row_bytes * rows, c->stream));
+    c->s_prezeroed = false;
+    c->have_sgm = false;
+    return SVA_OK;
+}
+
+int sva_frame_sgm_rows(sva_ctx* c, int32_t group, int32_t y0, int32_t rows, const void* state_in, void* state_out) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    if (!c->have_cost) return c->fail(SVA_ERR_STATE, "sgm_rows: no cost volume");
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(sva_run_sgm_rows(c, group, y0, rows, (const uint16_t*)state_in, (uint16_t*)state_out));
+    c->have_sgm = true;
+    return SVA_OK;
+}
+
 int sva_frame_wta_rows(sva_ctx* c, const void* s_rows_dev, int32_t y0, int32_t rows) {
-    if (!c || !s_rows_dev) return SVA_ERR_BAD_ARG;
+    if (!c) return SVA_ERR_BAD_ARG;
     if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    if (!s_rows_dev) {  // the context's own aggregation volume
+        if (!c->S.p || y0 < 0 || rows < 1 || y0 + rows > c->prm.height) return c->fail(SVA_ERR_BAD_ARG, "wta_rows: bad row block");
+        s_rows_dev = c->S.as<uint16_t>() + (size_t)y0 * c->prm.width * c->prm.num_disp;
+    }
     SVA_TRY(sva_run_wta_rows(c, (const uint16_t*)s_rows_dev, y0, rows));
     c->have_disp = true;
     return SVA_OK;

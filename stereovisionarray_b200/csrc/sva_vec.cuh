@@ -109,6 +109,10 @@ template <int BL> struct VecBlk4 {
         *reinterpret_cast<uint2*>(p) = make_uint2(r[0], r[1]);
         *reinterpret_cast<uint2*>(p + 4 * BL) = make_uint2(r[2], r[3]);
     }
+    static __device__ __forceinline__ void load(const uint16_t* p, uint32_t (&r)[4]) {
+        const uint2 a = *reinterpret_cast<const uint2*>(p), b = *reinterpret_cast<const uint2*>(p + 4 * BL);
+        r[0] = a.x; r[1] = a.y; r[2] = b.x; r[3] = b.y;
+    }
     static __device__ __forceinline__ void red(uint16_t* p, const uint32_t (&r)[4]) {
         unsigned long long v0 = ((unsigned long long)r[1] << 32) | r[0], v1 = ((unsigned long long)r[3] << 32) | r[2];
         asm volatile("red.global.add.u64 [%0], %1;" ::"l"(p), "l"(v0) : "memory");

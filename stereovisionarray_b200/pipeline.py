@@ -163,7 +163,17 @@ class DepthContext:
         return ptr.value, n.value
 
     def wta_rows(self, s_rows_ptr, y0, rows):
-        check(self._h, self._L.sva_frame_wta_rows(self._h, C.c_void_p(s_rows_ptr), int(y0), int(rows)))
+        """K3 on image rows [y0, y0 + rows) of S given by device pointer (None / 0: the context's own volume)"""
+        check(self._h, self._L.sva_frame_wta_rows(self._h, C.c_void_p(s_rows_ptr or None), int(y0), int(rows)))
+
+    def rows_begin(self, y0, rows):
+        """row-block pipeline: zero image rows [y0, y0 + rows) of the aggregation volume"""
+        check(self._h, self._L.sva_frame_rows_begin(self._h, int(y0), int(rows)))
+
+    def sgm_rows(self, group, y0, rows, state_in=0, state_out=0):
+        """one direction group (0 down-sweeping, 1 up-sweeping, 2 horizontal) on image rows [y0, y0 + rows); state_* = device pointers
+        to 3 * W * D u16 (0 = none: the sweep starts / ends in this block)"""
+        check(self._h, self._L.sva_frame_sgm_rows(self._h, int(group), int(y0), int(rows), C.c_void_p(state_in or None), C.c_void_p(state_out or None)))
 
     def download_disparity_rows(self, rows):
         p = self.params

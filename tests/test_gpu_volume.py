@@ -191,3 +191,38 @@ def test_bad_arguments_fail_loudly(ctx):
     p = abi.make_params(40, 32, 16, [(-1, 0)], win_half=2, n_paths=4, lr_gx=-1)
     disp, _ = ctx.depth_from_array(p, sc["ref"], sc["others"])
     assert disp.shape == (32, 40)
+
+
+@pytest.mark.parametrize("h,w,D,blocks", [(67, 96, 64, [(0, 20), (20, 47), (47, 67)]), (90, 140, 128, [(0, 9), (9, 10), (10, 55), (55, 90)]),
+                                           (64, 70, 256, [(0, 33), (33, 64)]), (58, 3840, 192, [(0, 30), (30, 58)])])
+def test_row_block_pipeline_emulated_on_one_gpu(ctx, h, w, D, blocks):
+    """the row-block scheme's building blocks (sva_frame_rows_begin / sva_frame_sgm_rows / sva_frame_wta_rows with the path-line state
+    handed from block to block) reproduce the whole-frame aggregation and maps bit for bit; blocks as small as one row, diagonals that
+    wrap at a block boundary, rows wide enough for ranged launches"""
+    import torch
+    sc = synth.make_scene(h, w, D, OFF8[:3] if w > 1000 else OFF8, 900 + D, face=True)
+    offs = OFF8[:3] if w > 1000 else OFF8
+    p = abi.make_params(w, h, D, offs, win_half=4, n_paths=8, lr_gx=-1)
+    ctx.set_debug(0, 0)
+    ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+    ctx.run(abi.STAGE_AD)
+    ctx.run(abi.STAGE_BOX)
+    ctx.run(abi.STAGE_SGM)
+    S_full = ctx.download_sgm()
+    d_full, s_full = ctx.download_disparity()
+    state = [torch.empty(3 * w * D, dtype=torch.int16, device="cuda") for _ in range(2)]
+    torch.cuda.synchronize()
+    for y0, y1 in blocks:
+        ctx.rows_begin(y0, y1 - y0)
+    for y0, y1 in blocks:
+        ctx.sgm_rows(2, y0, y1 - y0)
+    for i, (y0, y1) in enumerate(blocks):                      # down sweep: top block first
+        ctx.sgm_rows(0, y0, y1 - y0, state[(i + 1) % 2].data_ptr(), state[i % 2].data_ptr())
+    for i, (y0, y1) in enumerate(reversed(blocks)):            # up sweep: bottom block first
+        ctx.sgm_rows(1, y0, y1 - y0, state[(i + 1) % 2].data_ptr(), state[i % 2].data_ptr())
+    ctx.synchronize()
+    assert np.array_equal(ctx.download_sgm(), S_full)
+    for y0, y1 in blocks:
+        ctx.wta_rows(None, y0, y1 - y0)
+        d, s = ctx.download_disparity_rows(y1 - y0)
+        assert np.array_equal(d, d_full[y0:y1]) and np.array_equal(s, s_full[y0:y1])
