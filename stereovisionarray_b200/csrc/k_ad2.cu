@@ -42,6 +42,7 @@ struct Ad2Params {
     uint8_t img[SVA_MAX_PAIRS];         // index of the pair's view in imgs
     int ngroups;                        // pairs are staged in groups that fit the shared-memory budget
     uint8_t gbeg[SVA_MAX_PAIRS + 1];
+    int ty0;                            // first tile row of this launch (row-block pipeline; 0 for a whole frame)
 };
 
 // accumulate one pair into the thread's 16 disparities x 4 pixels; bp = word-aligned shared pointer of (this row, this quad, disparity 0)
@@ -80,7 +81,7 @@ k_ad_tile(const Ad2Params q) {
     __shared__ int4 s_geo[SVA_MAX_PAIRS];            // staged rectangle: offset in ad2_smem, pitch, rows
     const int t = threadIdx.x;
     const int quad = t & 31, sub = (t >> 5) & 1, yl = t >> 6;
-    const int x0 = blockIdx.x * AD2_TW, y0 = blockIdx.y * AD2_TH, da = blockIdx.z * AD2_DR;
+    const int x0 = blockIdx.x * AD2_TW, y0 = (blockIdx.y + q.ty0) * AD2_TH, da = blockIdx.z * AD2_DR;
     const int y = y0 + yl, x = x0 + 4 * quad;
     const uint32_t r = *reinterpret_cast<const uint32_t*>(q.ref + (size_t)y * q.rp + x);
     uint32_t ae[16], ao[16];
@@ -241,7 +242,11 @@ int sva_run_ad2(sva_ctx* ctx) {
     SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_ad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(ctx, "k_ad_tile");
-        k_ad_tile<<<dim3(div_up(W, AD2_TW), div_up(H, AD2_TH), div_up(D, AD2_DR)), AD2_THREADS, smem, ctx->stream>>>(q);
+        // a row block needs A on its rows and win_half rows either side (the box window); whole tiles, clipped to the image
+        int ya = 0, yb = H;
+        if (ctx->win_rows > 0) { ya = std::max(0, ctx->win_y0 - p.win_half); yb = std::min(H, ctx->win_y0 + ctx->win_rows + p.win_half); }
+        q.ty0 = ya / AD2_TH;
+        k_ad_tile<<<dim3(div_up(W, AD2_TW), div_up(yb, AD2_TH) - q.ty0, div_up(D, AD2_DR)), AD2_THREADS, smem, ctx->stream>>>(q);
     }
     SVA_CUDA_OK(ctx, cudaGetLastError());
     ctx->have_ad = true;

@@ -217,6 +217,7 @@ struct BoxPParams {
     int gxp, gxn, gyp, gyn;
     int band_rows, txo, wp;
     long long row_words;
+    int ry0, ry1;  // output rows [ry0, ry1) (the whole image, or a row block)
 };
 
 __global__ void __launch_bounds__(256, 2)
@@ -229,7 +230,7 @@ k_box_planar(BoxPParams q) {
     const int dpc = min((int)blockIdx.y * BXP_WARPS + warp, (D >> 1) - 1);  // warps beyond D/2 (D % 16 != 0) redo the last pair; never stored
     const int d = 2 * dpc;
     const int xs = blockIdx.x * q.txo - q.kk;  // image x of strip column 0
-    const int y0 = blockIdx.z * q.band_rows, y1 = min(H, y0 + q.band_rows);
+    const int y0 = q.ry0 + blockIdx.z * q.band_rows, y1 = min(q.ry1, y0 + q.band_rows);
     for (int i = t; i < y1 - y0; i += 256) s_limy[i] = axis_limit(y0 + i, H, k, q.gyp, q.gyn);
 
     int thr[8], thrmin = 0x7FFFFFFF;  // validity slack of each column for this warp's even disparity
@@ -378,11 +379,14 @@ static int sva_launch_box_planar(sva_ctx* ctx) {
     const int slots = per_sm * ctx->sm_count, per_band = strips * dgroups;
     int bands = 1;
     double best = 1e30;
-    for (int b = 1; b <= H && b <= 4096; b++) {
-        const int rows = div_up(H, b);
+    q.ry0 = 0; q.ry1 = H;
+    if (ctx->win_rows > 0) { q.ry0 = ctx->win_y0; q.ry1 = ctx->win_y0 + ctx->win_rows; }
+    const int Hw = q.ry1 - q.ry0;
+    for (int b = 1; b <= Hw && b <= 4096; b++) {
+        const int rows = div_up(Hw, b);
         if (rows > BXP_MAX_BAND) continue;
         if (b > 1 && rows < k) break;
-        const int nb = div_up(H, rows);
+        const int nb = div_up(Hw, rows);
         const double cost = (double)div_up(nb * per_band, slots) * (rows + 2 * k - 1 + 8);
         if (cost < best) { best = cost; bands = nb; q.band_rows = rows; }
     }

@@ -56,6 +56,7 @@ int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, c
     for (int i = 0; i < p->n_pairs; i++) SVA_TRY(check_image(c, &others[i], W, H, "other view"));
     if (mask) SVA_TRY(check_image(c, mask, W, H, "mask"));
     c->prm = *p;
+    c->win_y0 = 0; c->win_rows = 0;
     c->pair_begin = 0; c->pair_end = p->n_pairs;
     c->have_frame = c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;
     const size_t img = (size_t)W * H;
@@ -305,6 +306,7 @@ int sva_frame_set_params(sva_ctx* c, const sva_params* p) {
     SVA_TRY(check_params(c, p));
     if (p->width != c->prm.width || p->height != c->prm.height) return c->fail(SVA_ERR_BAD_ARG, "set_params cannot change the image size");
     c->prm = *p;
+    c->win_y0 = 0; c->win_rows = 0;
     c->pair_begin = 0; c->pair_end = p->n_pairs;
     c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;  // volumes of the old disparity range are not valid for the new one
     return SVA_OK;
@@ -332,6 +334,7 @@ int sva_frame_rows_begin(sva_ctx* c, int32_t y0, int32_t rows) {
     SVA_CUDA_OK(c, cudaMemsetAsync((uint8_t*)c->S.p + row_bytes * y0, 0, row_bytes * rows, c->stream));
     c->s_prezeroed = false;
     c->have_sgm = false;
+    c->win_y0 = y0; c->win_rows = rows == p.height ? 0 : rows;  // SVA_STAGE_AD / SVA_STAGE_BOX now compute what this block needs
     return SVA_OK;
 }
 

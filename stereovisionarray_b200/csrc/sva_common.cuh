@@ -107,6 +107,7 @@ struct sva_ctx {
     ApGeom ap;
     uint64_t ap_zero_key = 0;  // geometry + buffer the zero borders of AP were last established for
     DevBuf staging_host;  // pinned host staging for image uploads / result downloads
+    int win_y0 = 0, win_rows = 0;  // row-block pipeline: K1a / K1b compute only what image rows [win_y0, win_y0 + win_rows) need (0 rows = whole frame)
     bool guard = false;   // debug: new device allocations get canary bands on both sides and a poisoned interior (sva_debug_set_guard)
     void device_bufs(std::vector<DevBuf*>& out);
     void release(DevBuf& b);

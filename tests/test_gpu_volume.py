@@ -210,10 +210,21 @@ def test_row_block_pipeline_emulated_on_one_gpu(ctx, h, w, D, blocks):
     ctx.run(abi.STAGE_SGM)
     S_full = ctx.download_sgm()
     d_full, s_full = ctx.download_disparity()
+    C_full = ctx.download_cost()
     state = [torch.empty(3 * w * D, dtype=torch.int16, device="cuda") for _ in range(2)]
     torch.cuda.synchronize()
-    for y0, y1 in blocks:
-        ctx.rows_begin(y0, y1 - y0)
+    # the cost volume block by block on a second, poisoned context (bottom block first: a block must not lean on its neighbours' rows)
+    from stereovisionarray_b200.pipeline import DepthContext
+    blk = DepthContext(0)
+    blk.set_guard(True)
+    blk.upload(p, sc["ref"], sc["others"], sc["mask"])
+    for y0, y1 in reversed(blocks):
+        blk.rows_begin(y0, y1 - y0)
+        blk.run(abi.STAGE_AD)
+        blk.run(abi.STAGE_BOX)
+        assert np.array_equal(blk.download_cost()[y0:y1], C_full[y0:y1]), "cost rows %d..%d" % (y0, y1)
+    assert blk.check_guards()[1] == 0
+    full, ctx = ctx, blk
     for y0, y1 in blocks:
         ctx.sgm_rows(2, y0, y1 - y0)
     for i, (y0, y1) in enumerate(blocks):                      # down sweep: top block first
@@ -226,3 +237,5 @@ def test_row_block_pipeline_emulated_on_one_gpu(ctx, h, w, D, blocks):
         ctx.wta_rows(None, y0, y1 - y0)
         d, s = ctx.download_disparity_rows(y1 - y0)
         assert np.array_equal(d, d_full[y0:y1]) and np.array_equal(s, s_full[y0:y1])
+    assert blk.check_guards()[1] == 0
+    blk.close()
