@@ -279,9 +279,12 @@ def run_pair_sharded(args, rank, local_rank, world):
     ctx.set_stream(stream.cuda_stream)
     b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
     slices = args.c3_scheme == "slices" and world > 1  # one GPU: nothing to exchange, the frame runs as one plain pipeline
+    rows = args.c3_scheme == "rows" and world > 1
     keep = {}
     if slices:
         ctx.upload(sdist.slice_params(p, rank, world), sc["ref"], sc["others"], sc["mask"])
+    elif rows:
+        ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
     else:
         ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
         ptr, nbytes = ctx.ad_device_ptr()
@@ -290,6 +293,9 @@ def run_pair_sharded(args, rank, local_rank, world):
     def step():
         if slices:
             sdist.slice_sharded_compute(ctx, p, rank, world, None, keep)
+            return
+        if rows:
+            sdist.row_sharded_compute(ctx, p, rank, world, None, keep)
             return
         if e > b:
             ctx.set_pair_range(b, e)
@@ -336,6 +342,8 @@ def run_pair_sharded(args, rank, local_rank, world):
                           "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths,
                           "partitioning": ("disparity slices of %d (cost volume, no reduction) -> all-gather -> path directions %s -> reduce-scatter by row blocks -> "
                                            "row-sharded WTA; %d ranks" % (p.num_disp // world, sdist.direction_masks(p.n_paths, world), world)) if slices else
+                                          ("row blocks %s end to end: cost volume and horizontal paths local, row-sweeping paths as a pipeline handing %.1f MB of path state per hop; no volume collective"
+                                           % (sdist.row_blocks(p.height, world)[1], 3 * p.width * p.num_disp * 2 / 1e6)) if rows else
                                           ("single GPU: the whole frame, no exchange" if world == 1 else
                                            "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9)),
                           "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
@@ -479,7 +487,7 @@ def main():
     ap.add_argument("--cpu-band", type=int, default=256, help="rows of the CPU-baseline sample")
     ap.add_argument("--ref-band", type=int, default=44, help="rows per band of the reference arm (40 + valid rows)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--c3-scheme", default="slices", choices=["pairs", "slices"],
+    ap.add_argument("--c3-scheme", default="slices", choices=["pairs", "slices", "rows"],
                     help="c3 only: 'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding (DESIGN.md §7)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "sva" else args.warmup

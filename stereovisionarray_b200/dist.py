@@ -1,6 +1,6 @@
 """Multi-GPU sharding of the depth path on one 8xB200 box — one process per GPU, torch.distributed for plumbing.
 
-Two natural partitions, nothing else:
+Natural partitions, nothing else:
   * frames of a capture batch are independent units -> rank r takes frames [r*F/G, (r+1)*F/G); NO data-path collective;
   * camera pairs of ONE frame: the cost volume is a sum over pairs (integer, associative, commutative), so each rank
     computes the AD partial of its pair range over the full [H][W][D] volume and the partials are sum-reduced onto the
@@ -175,6 +175,95 @@ def slice_sharded_depth(ctx, p, ref, others, mask, rank, world, group=None, keep
     disp = torch.cat(d_all)[:p.height].cpu().numpy().astype(np.uint16)
     sub = torch.cat(s_all)[:p.height].cpu().numpy()
     return disp, sub
+
+
+def row_pipeline_steps(rank, world):
+    """Hop schedule of the row-block pipeline.  Step s (0 <= s < world - 1) moves the down-sweep state from rank s to s + 1 and the
+    up-sweep state from rank world - 1 - s to world - 2 - s.  Returns, per step, what THIS rank does:
+    (send_down_to, recv_down_from, send_up_to, recv_up_from), None where it takes no part.  Every rank walks the steps in the same
+    order and issues a step's transfers as one batch, so two neighbours that exchange both states in the same step (the middle of
+    the array) cannot dead-lock."""
+    steps = []
+    for s in range(world - 1):
+        steps.append((s + 1 if rank == s else None, s if rank == s + 1 else None,
+                      world - 2 - s if rank == world - 1 - s else None, world - 1 - s if rank == world - 2 - s else None))
+    return steps
+
+
+def row_sharded_compute(ctx, p, rank, world, group=None, keep=None, device="cuda"):
+    """Device part of row_sharded_depth for a frame already uploaded on every rank: the rank's block of image rows end to end.
+    Afterwards the block's maps are in the library (ctx.download_disparity_rows).  Returns (y0, y1)."""
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    keep = keep if keep is not None else {}
+    _, blocks = row_blocks(p.height, world)
+    if any(b[1] <= b[0] for b in blocks):
+        raise ValueError("row-block pipeline: %d rows do not give every one of %d ranks a block" % (p.height, world))
+    y0, y1 = blocks[rank]
+    n = y1 - y0
+    words = 3 * p.width * p.num_disp // 2  # u16 pairs as int32: NCCL has no 16-bit integer type
+    if keep.get("state") is None or keep["state"][0].numel() != words or keep["state"][0].device.type != torch.device(device).type:
+        keep["state"] = [torch.empty(words, dtype=torch.int32, device=device) for _ in range(4)]
+    d_in, d_out, u_in, u_out = keep["state"]
+    ctx.rows_begin(y0, n)
+    ctx.run(abi.STAGE_AD)
+    ctx.run(abi.STAGE_BOX)
+    ctx.sgm_rows(2, y0, n)
+    if rank == 0:
+        ctx.sgm_rows(0, y0, n, 0, d_out.data_ptr())
+    if rank == world - 1:
+        ctx.sgm_rows(1, y0, n, 0, u_out.data_ptr())
+    for send_d, recv_d, send_u, recv_u in row_pipeline_steps(rank, world):
+        ops = []
+        if send_d is not None:
+            ops.append(dist.P2POp(dist.isend, d_out, send_d, group))
+        if recv_d is not None:
+            ops.append(dist.P2POp(dist.irecv, d_in, recv_d, group))
+        if send_u is not None:
+            ops.append(dist.P2POp(dist.isend, u_out, send_u, group))
+        if recv_u is not None:
+            ops.append(dist.P2POp(dist.irecv, u_in, recv_u, group))
+        if ops:
+            for r in dist.batch_isend_irecv(ops):
+                r.wait()
+        if recv_d is not None:
+            ctx.sgm_rows(0, y0, n, d_in.data_ptr(), d_out.data_ptr())
+        if recv_u is not None:
+            ctx.sgm_rows(1, y0, n, u_in.data_ptr(), u_out.data_ptr())
+    ctx.wta_rows(None, y0, n)
+    return y0, y1
+
+
+def row_sharded_depth(ctx, p, ref, others, mask, rank, world, group=None, keep=None):
+    """One frame sharded by ROW BLOCKS end to end — no volume ever crosses GPUs (c3):
+      1. rank r computes the cost volume of its block of image rows (K1a + K1b; the box window reaches win_half rows into the neighbours'
+         rows of the IMAGES, which every rank holds — nothing is exchanged);
+      2. the horizontal path directions are local to a row;
+      3. the three down-sweeping directions run as a pipeline 0 -> G-1, the three up-sweeping ones as a pipeline G-1 -> 0: a rank
+         aggregates its block and hands L of every path line at its last row (3 * W * D u16, a few MB) to the next rank;
+      4. K3 on the rank's rows; the maps are gathered on rank 0.
+    Every rank holds the frame's images.  ctx must run on torch's current stream.  Returns (disp, subpix) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    ctx.upload(p, ref, others, mask)
+    y0, y1 = row_sharded_compute(ctx, p, rank, world, group, keep)
+    rows_per = row_blocks(p.height, world)[0]
+    d_t = torch.full((rows_per, p.width), abi.SVA_DISP_INVALID, dtype=torch.int32)
+    s_t = torch.full((rows_per, p.width), -1.0, dtype=torch.float32)
+    d, s = ctx.download_disparity_rows(y1 - y0)
+    d_t[:y1 - y0] = torch.from_numpy(d.astype(np.int32))
+    s_t[:y1 - y0] = torch.from_numpy(s)
+    if world == 1:
+        return d_t[:p.height].numpy().astype(np.uint16), s_t[:p.height].numpy()
+    d_all = [torch.empty_like(d_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    s_all = [torch.empty_like(s_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    dist.gather(d_t.cuda(), d_all, dst=0, group=group)
+    dist.gather(s_t.cuda(), s_all, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat(d_all)[:p.height].cpu().numpy().astype(np.uint16), torch.cat(s_all)[:p.height].cpu().numpy()
 
 
 def numpy_pack(a_u16):

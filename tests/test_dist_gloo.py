@@ -111,3 +111,94 @@ def test_slice_direction_row_plans():
     import pytest
     with pytest.raises(ValueError):
         sdist.slice_params(p, 0, 3)
+
+
+class _ToyRowsBackend:
+    """Stands in for DepthContext in the row-block pipeline: the same calls (rows_begin / run / sgm_rows / wta_rows, state buffers by
+    address), a toy recurrence instead of SGM.  A sweep's state after row y is L(y) = (L(y-1) * (slot + 2) + c(y)) mod 251 per element,
+    and S(y) accumulates every L(y): the result depends on every hop delivering the right predecessor's state, in the right order."""
+
+    def __init__(self, p):
+        self.p = p
+        self.n = 3 * p.width * p.num_disp
+        self.S = np.zeros(p.height, np.int64)
+        self.log = []
+
+    def _buf(self, ptr):
+        import ctypes
+        return np.ctypeslib.as_array((ctypes.c_int16 * self.n).from_address(ptr))
+
+    def rows_begin(self, y0, rows):
+        self.S[y0:y0 + rows] = 0
+
+    def run(self, stage):
+        self.log.append(stage)
+
+    def sgm_rows(self, group, y0, rows, state_in=0, state_out=0):
+        if group == 2:
+            self.S[y0:y0 + rows] += 7
+            return
+        mult = np.repeat(np.arange(3) + 2, self.n // 3).astype(np.int64)
+        first = (y0 == 0) if group == 0 else (y0 + rows == self.p.height)
+        L = np.zeros(self.n, np.int64) if first else self._buf(state_in).astype(np.int64)
+        ys = range(y0, y0 + rows) if group == 0 else range(y0 + rows - 1, y0 - 1, -1)
+        for y in ys:
+            L = (L * mult + (y * 13 + group * 5 + 1)) % 251
+            self.S[y] += int(L.sum())
+        if state_out:
+            self._buf(state_out)[:] = L.astype(np.int16)
+
+    def wta_rows(self, ptr, y0, rows):
+        self.log.append(("wta", y0, rows))
+
+
+def _rows_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        p = abi.make_params(12, 23, 8, [(-1, 0)], win_half=2)
+        be = _ToyRowsBackend(p)
+        keep = {}
+        for _ in range(2):  # twice: the state buffers are reused across frames
+            y0, y1 = sdist.row_sharded_compute(be, p, rank, world, None, keep, device="cpu")
+        mine = torch.zeros(p.height, dtype=torch.int64)
+        mine[y0:y1] = torch.from_numpy(be.S[y0:y1])
+        dist.all_reduce(mine)
+        if rank == 0:
+            one = _ToyRowsBackend(p)
+            one.rows_begin(0, p.height)
+            one.sgm_rows(2, 0, p.height)
+            one.sgm_rows(0, 0, p.height)
+            one.sgm_rows(1, 0, p.height)
+            q.put(bool(np.array_equal(mine.numpy(), one.S)) and be.log[-1] == ("wta", y0, y1 - y0))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3, 4])
+def test_row_block_pipeline_hops(world):
+    """dist.row_sharded_compute over gloo: every block continues the sweeps from the state its neighbour handed over (down 0 -> G-1,
+    up G-1 -> 0, both in flight at once), and the assembled result equals the single-process run"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(120)
+        assert p.exitcode == 0
+    assert q.get(timeout=10)
+
+
+def test_row_pipeline_schedule():
+    for world in (1, 2, 3, 4, 8):
+        plans = [sdist.row_pipeline_steps(r, world) for r in range(world)]
+        assert all(len(pl) == max(0, world - 1) for pl in plans)
+        for s in range(world - 1):
+            sends = [(r, plans[r][s][0]) for r in range(world) if plans[r][s][0] is not None] + [(r, plans[r][s][2]) for r in range(world) if plans[r][s][2] is not None]
+            recvs = [(plans[r][s][1], r) for r in range(world) if plans[r][s][1] is not None] + [(plans[r][s][3], r) for r in range(world) if plans[r][s][3] is not None]
+            assert sorted(sends) == sorted(recvs) == sorted([(s, s + 1), (world - 1 - s, world - 2 - s)])
+    with pytest.raises(ValueError):
+        sdist.row_sharded_compute(None, abi.make_params(16, 10, 8, [(-1, 0)], win_half=2), 0, 16)

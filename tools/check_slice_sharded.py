@@ -1,4 +1,5 @@
-"""torchrun check: dist.slice_sharded_depth over WORLD_SIZE GPUs == the single-GPU one-call path, bit for bit (rank 0 compares)."""
+"""torchrun check: dist.slice_sharded_depth and dist.row_sharded_depth over WORLD_SIZE GPUs == the single-GPU one-call path, bit for bit
+(rank 0 compares)."""
 import os
 import sys
 
@@ -25,12 +26,16 @@ for (h, w, D, off, k) in [(270, 480, 256, OFF15, 20), (203, 333, 64 * world // (
     keep = {}
     for rep in range(2):  # twice: cached buffers, re-upload
         out = sdist.slice_sharded_depth(ctx, p, sc["ref"], sc["others"], sc["mask"], rank, world, None, keep)
+    keep_rows = {}
+    for rep in range(2):
+        out_rows = sdist.row_sharded_depth(ctx, p, sc["ref"], sc["others"], sc["mask"], rank, world, None, keep_rows)
     if rank == 0:
         ref = DepthContext(local)
         d0, s0 = ref.depth_from_array(p, sc["ref"], sc["others"], sc["mask"])
-        same = np.array_equal(out[0], d0) and np.array_equal(out[1], s0)
-        print("slice-sharded %dx%dx%d over %d GPUs: %s (valid %.3f)" % (w, h, D, world, "bit-exact" if same else "MISMATCH", float((d0 != 0xFFFF).mean())))
-        ok = ok and same
+        for name, o in (("slice-sharded", out), ("row-sharded", out_rows)):
+            same = np.array_equal(o[0], d0) and np.array_equal(o[1], s0)
+            print("%s %dx%dx%d over %d GPUs: %s (valid %.3f)" % (name, w, h, D, world, "bit-exact" if same else "MISMATCH", float((d0 != 0xFFFF).mean())))
+            ok = ok and same
         ref.close()
     ctx.close()
 dist.barrier()
