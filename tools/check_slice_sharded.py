@@ -38,6 +38,32 @@ for (h, w, D, off, k) in [(270, 480, 256, OFF15, 20), (203, 333, 64 * world // (
             ok = ok and same
         ref.close()
     ctx.close()
+if len(sys.argv) > 1:  # e.g. 3840x2160x256: time the row-block pipeline on a frame of random pixels of that size (15 pairs), device time, max over ranks
+    w, h, D = (int(v) for v in sys.argv[1].split("x"))
+    rng = np.random.default_rng(5)
+    ref_img = rng.integers(0, 256, (h, w), dtype=np.uint8)
+    others = [rng.integers(0, 256, (h, w), dtype=np.uint8) for _ in OFF15]
+    p = abi.make_params(w, h, D, OFF15, win_half=20, n_paths=8, lr_gx=-1)
+    ctx = DepthContext(local)
+    stream = torch.cuda.current_stream()
+    ctx.set_stream(stream.cuda_stream)
+    ctx.upload(p, ref_img, others, None)
+    keep = {}
+    for _ in range(2):
+        sdist.row_sharded_compute(ctx, p, rank, world, None, keep)
+    torch.cuda.synchronize()
+    dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(3):
+        sdist.row_sharded_compute(ctx, p, rank, world, None, keep)
+    e1.record(stream)
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / 3], dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    if rank == 0:
+        print("row-block pipeline %dx%dx%d, 15 pairs, %d GPUs: %.2f ms per frame (random pixels)" % (w, h, D, world, float(t.item())))
+    ctx.close()
 dist.barrier()
 dist.destroy_process_group()
 sys.exit(0 if ok else 1)
