@@ -487,8 +487,9 @@ def main():
     ap.add_argument("--cpu-band", type=int, default=256, help="rows of the CPU-baseline sample")
     ap.add_argument("--ref-band", type=int, default=44, help="rows per band of the reference arm (40 + valid rows)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--c3-scheme", default="slices", choices=["pairs", "slices", "rows"],
-                    help="c3 only: 'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding (DESIGN.md §7)")
+    ap.add_argument("--c3-scheme", default="rows", choices=["pairs", "slices", "rows"],
+                    help="c3 only: 'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding; "
+                         "'rows' = row blocks end to end, row-sweeping paths as a pipeline between neighbours (DESIGN.md §7)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "sva" else args.warmup
     with StdoutToStderr():
