@@ -93,7 +93,7 @@ def test_pair_sharded_reduce_and_frame_partition(world):
 
 def test_slice_direction_row_plans():
     """host-side plans of dist.slice_sharded_depth (pure Python; the device path is covered by tests/test_gpu_volume.py and, over real
-    GPUs, by tools/check_slice_sharded.py under torchrun)"""
+    GPUs, by tools/check_sharded.py under torchrun)"""
     from stereovisionarray_b200 import abi, dist as sdist
     for world in (1, 2, 4, 8):
         masks = sdist.direction_masks(8, world)
