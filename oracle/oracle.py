@@ -169,6 +169,14 @@ class Oracle:
         assert rc == 0, rc
         return L
 
+    def sgm_rows(self, p, Cv, dir_index, y0, rows, prev_in, S, prev_out):
+        """one row-sweeping direction on image rows [y0, y0 + rows), added into S in place; prev_in / prev_out: [W][D] u16 or None"""
+        Cv = np.ascontiguousarray(Cv, dtype=np.uint16)
+        assert S.dtype == np.uint16 and S.flags.c_contiguous
+        rc = self.lib.orc_sgm_rows(C.byref(p), _ptr(Cv, C.c_uint16), dir_index, y0, rows, _ptr(prev_in, C.c_uint16) if prev_in is not None else None,
+                                   _ptr(S, C.c_uint16), _ptr(prev_out, C.c_uint16) if prev_out is not None else None)
+        assert rc == 0, rc
+
     def sgm_aggregate(self, p, Cv, n_use=None):
         Cv = np.ascontiguousarray(Cv, dtype=np.uint16)
         S = np.zeros(self._shape(p), dtype=np.uint16)

@@ -442,6 +442,35 @@ static void sgm_path_add(const sva_params* p, const uint16_t* C, int dx, int dy,
     }
     free(prev); free(cur);
 }
+/* The row-sweeping part of sgm_path_add restricted to image rows [y0, y0 + rows): the restatement of the multi-GPU row-block pipeline
+ * (DESIGN.md §7).  prev_in = L of the row the sweep visited just before the block ([W][D], indexed by image column; NULL when the block
+ * starts the sweep), prev_out receives L of the block's last row in sweep order.  Splitting the row loop of sgm_path_add at block
+ * boundaries and carrying `prev` across is all there is to it. */
+int orc_sgm_rows(const sva_params* p, const uint16_t* C, int32_t dir_index, int32_t y0, int32_t rows, const uint16_t* prev_in, uint16_t* S,
+                 uint16_t* prev_out) {
+    if (!params_ok(p) || dir_index < 0 || dir_index > 7 || y0 < 0 || rows < 1 || y0 + rows > p->height) return SVA_ERR_BAD_ARG;
+    const int W = p->width, H = p->height, D = p->num_disp, dx = ORC_DIRS[dir_index][0], dy = ORC_DIRS[dir_index][1];
+    if (dy == 0) return SVA_ERR_BAD_ARG; /* horizontal paths are row-local: use orc_sgm_single_path on the rows */
+    const size_t row = (size_t)W * D;
+    uint16_t* prev = (uint16_t*)malloc(row * sizeof(uint16_t));
+    uint16_t* cur = (uint16_t*)malloc(row * sizeof(uint16_t));
+    if (prev_in) memcpy(prev, prev_in, row * sizeof(uint16_t));
+    for (int yi = 0; yi < rows; yi++) {
+        int y = dy > 0 ? y0 + yi : y0 + rows - 1 - yi, py = y - dy;
+        for (int x = 0; x < W; x++) {
+            int px = x - dx;
+            int border = (px < 0 || px >= W || py < 0 || py >= H);
+            if (!border && !prev_in && yi == 0) { free(prev); free(cur); return SVA_ERR_BAD_ARG; } /* the block continues a sweep: state needed */
+            sgm_cell_row(p, C + ((size_t)y * W + x) * D, border ? NULL : prev + (size_t)px * D, cur + (size_t)x * D);
+        }
+        uint16_t* s = S + (size_t)y * row;
+        for (size_t i = 0; i < row; i++) s[i] = (uint16_t)(s[i] + cur[i]);
+        uint16_t* t = prev; prev = cur; cur = t;
+    }
+    if (prev_out) memcpy(prev_out, prev, row * sizeof(uint16_t));
+    free(prev); free(cur);
+    return SVA_OK;
+}
 /* one path on its own: L_out = L_r (for unit tests) */
 int orc_sgm_single_path(const sva_params* p, const uint16_t* C, int32_t dir_index, uint16_t* L_out) {
     if (!params_ok(p) || dir_index < 0 || dir_index > 7) return SVA_ERR_BAD_ARG;

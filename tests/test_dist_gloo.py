@@ -202,3 +202,80 @@ def test_row_pipeline_schedule():
             assert sorted(sends) == sorted(recvs) == sorted([(s, s + 1), (world - 1 - s, world - 2 - s)])
     with pytest.raises(ValueError):
         sdist.row_sharded_compute(None, abi.make_params(16, 10, 8, [(-1, 0)], win_half=2), 0, 16)
+
+
+class _OracleRowsBackend:
+    """DepthContext's row-block calls served by the CPU oracle (tests may use it): real SGM through dist.row_sharded_compute.  The state
+    crossing a block boundary is the oracle's own — L of the previous row by image column, three directions — in the same 3 * W * D u16."""
+    GROUPS = {0: (0, 4, 5), 1: (1, 6, 7)}
+
+    def __init__(self, orc, p, Cv):
+        self.orc, self.p, self.C = orc, p, Cv
+        self.S = np.zeros((p.height, p.width, p.num_disp), np.uint16)
+        self.wta = []
+
+    def _state(self, ptr):
+        import ctypes
+        n = 3 * self.p.width * self.p.num_disp
+        return np.ctypeslib.as_array((ctypes.c_uint16 * n).from_address(ptr)).reshape(3, self.p.width, self.p.num_disp)
+
+    def rows_begin(self, y0, rows):
+        self.S[y0:y0 + rows] = 0
+
+    def run(self, stage):
+        pass  # the cost volume is given
+
+    def sgm_rows(self, group, y0, rows, state_in=0, state_out=0):
+        p = self.p
+        if group == 2:
+            for di in (2, 3):
+                self.S[y0:y0 + rows] += self.orc.sgm_single_path(p, self.C, di)[y0:y0 + rows]  # horizontal paths are row-local
+            return
+        first = (y0 == 0) if group == 0 else (y0 + rows == p.height)
+        for slot, di in enumerate(self.GROUPS[group]):
+            pin = None if first else np.ascontiguousarray(self._state(state_in)[slot])
+            pout = np.zeros((p.width, p.num_disp), np.uint16)
+            self.orc.sgm_rows(p, self.C, di, y0, rows, pin, self.S, pout)
+            if state_out:
+                self._state(state_out)[slot] = pout
+
+    def wta_rows(self, ptr, y0, rows):
+        self.wta.append((y0, rows))
+
+
+def _oracle_rows_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle.oracle import Oracle
+        orc = Oracle()
+        h, w, D = 37, 44, 16
+        sc = synth.make_scene(h, w, D, [(-1, 0), (1, 1)], 91)
+        p = abi.make_params(w, h, D, [(-1, 0), (1, 1)], win_half=3, n_paths=8, lr_gx=-1)
+        Cv = orc.box_cost(p, orc.ad_volume(p, sc["ref"], sc["others"]))
+        be = _OracleRowsBackend(orc, p, Cv)
+        y0, y1 = sdist.row_sharded_compute(be, p, rank, world, None, {}, device="cpu")
+        mine = torch.zeros(be.S.shape, dtype=torch.int32)
+        mine[y0:y1] = torch.from_numpy(be.S[y0:y1].astype(np.int32))
+        dist.all_reduce(mine)
+        if rank == 0:
+            q.put(bool(np.array_equal(mine.numpy().astype(np.uint16), orc.sgm_aggregate(p, Cv))))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_row_block_pipeline_with_the_oracle_recurrence(world):
+    """the row-block scheme with the real SGM recurrence (oracle) in every process: the blocks' aggregation volumes assemble to the
+    whole-frame oracle aggregation — the scheme is exact, independent of the CUDA kernels"""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_oracle_rows_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    assert q.get(timeout=10)
