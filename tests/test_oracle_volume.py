@@ -184,3 +184,26 @@ def test_literal_equals_volume_wta_on_a_rectified_pair(oracle):
             assert lit[y, x] == lo + int(np.argmin(seg))
             checked += 1
     assert checked > 500
+
+
+def test_sgm_rows_blocks_equal_the_whole_path(oracle):
+    """orc_sgm_rows (the restatement of the multi-GPU row-block sweep): any cut of the rows into blocks, with L of the previous row carried
+    across, adds up to exactly the whole-frame path — for every row-sweeping direction, blocks of one row included"""
+    sc, p = _scene(29, 36, 16, [(-1, 0), (1, 1)], 23, win_half=3, n_paths=8)
+    Cv = oracle.box_cost(p, oracle.ad_volume(p, sc["ref"], sc["others"]))
+    rng = np.random.default_rng(4)
+    for di in (0, 1, 4, 5, 6, 7):
+        whole = oracle.sgm_single_path(p, Cv, di)
+        cuts = sorted(set(rng.integers(1, p.height, 4).tolist()) | {1, p.height - 1})
+        blocks = list(zip([0] + cuts, cuts + [p.height]))
+        down = di in (0, 4, 5)
+        S = np.zeros_like(whole)
+        state = None
+        for y0, y1 in (blocks if down else reversed(blocks)):
+            out = np.zeros((p.width, p.num_disp), np.uint16)
+            oracle.sgm_rows(p, Cv, di, y0, y1 - y0, state, S, out)
+            state = out
+        assert np.array_equal(S, whole), "direction %d" % di
+    # a block that continues a sweep refuses to run without the state
+    with pytest.raises(AssertionError):
+        oracle.sgm_rows(p, Cv, 0, 5, 4, None, np.zeros_like(whole), None)
