@@ -129,6 +129,8 @@ static int run_stage(sva_ctx* c, int stage) {
             return sva_run_box(c, false);
         case SVA_STAGE_SGM:
             if (!c->have_cost) return c->fail(SVA_ERR_STATE, "cost volume not computed");
+            if (c->win_rows > 0)  // only the block's rows of the cost volume exist
+                return c->fail(SVA_ERR_STATE, "a row block is active (sva_frame_rows_begin): use sva_frame_sgm_rows, or upload the frame again for a whole-frame run");
             return sva_run_sgm(c);
         case SVA_STAGE_ALL:
             SVA_TRY(prezero_s(c));
