@@ -77,14 +77,14 @@ std::vector<std::array<int, 2>> getCameraPairs(const std::vector<Camera>& camera
     int32_t out[128];
     int n = sva_get_camera_pairs((int)cameras.size(), (int)pairs, -1, out, 64);
     std::vector<std::array<int, 2>> r;
-    for (int i = 0; i < n; i++) r.push_back({out[2 * i], out[2 * i + 1]});
+    for (int i = 0; i < n && i < 64; i++) r.push_back({out[2 * i], out[2 * i + 1]});  // n may exceed the capacity; only 64 pairs were written
     return r;
 }
 std::vector<std::array<int, 2>> getCameraPairs(const std::vector<Camera>& cameras, const pairType pair, int cameraNum) {  // functions.h:36
     int32_t out[128];
     int n = sva_get_camera_pairs((int)cameras.size(), (int)pair, cameraNum, out, 64);
     std::vector<std::array<int, 2>> r;
-    for (int i = 0; i < n; i++) r.push_back({out[2 * i], out[2 * i + 1]});
+    for (int i = 0; i < n && i < 64; i++) r.push_back({out[2 * i], out[2 * i + 1]});  // n may exceed the capacity; only 64 pairs were written
     return r;
 }
 

@@ -3,7 +3,7 @@
 
   python bench.py --gpus N --steps K --warmup W [--config c1] [--win-half 20] [--impl reference]
 
-A step = one pass of the hot path (K1a AD volume -> K1b box/pack -> 8-path SGM with fused WTA/LR/sub-pixel) over one synthetic
+A step = one pass of the hot path (K1a AD volume -> K1b box/pack -> 8-path SGM -> WTA/LR/sub-pixel) over one synthetic
 frame per rank.  `value` = whole-job MDE/s with inputs resident in HBM (CUDA events on the library's stream, max over ranks);
 `e2e` = the same metric through the host-buffer C-ABI call sva_depth_from_array (pinned host inputs, H2D + D2H inside the timed
 region).  Volumes (>= 300 MB each at c1) exceed the 126 MB L2, so no L2 flush is needed between iterations.

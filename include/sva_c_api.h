@@ -5,7 +5,7 @@
  * Every entry point is `extern "C"`, takes plain pointers + sizes, returns an int status
  * (0 = SVA_OK, negative = sva_status) and never retains a caller pointer after it returns.
  * The reference has no error codes (failures are cv::Exception / UB); the adapter
- * in include/sva_reference_api.hpp turns a non-zero status back into an exception.
+ * in adapter/sva_functions.cpp turns a non-zero status back into an exception.
  *
  * Citations `file:line` are into the reference tree (Nahuel-M/StereoVisionArray).
  * Images are 8-bit, single channel, row-major: (data, rows, cols, step_bytes) == cv::Mat
@@ -177,7 +177,7 @@ int sva_stream_elapsed(sva_ctx* ctx, int64_t ticket, float* out_ms);
 typedef enum sva_stage {
     SVA_STAGE_AD = 1,        /* K1a: A(y,x,d) = sum_k |R - I_k(shifted)|            -> u16 [H][W][D] */
     SVA_STAGE_BOX = 2,       /* K1b: 2k x 2k box sum + shift/cap + validity          -> u16 [H][W][D] (C) */
-    SVA_STAGE_SGM = 3,       /* K2 (+ fused K3 in its last pass): S and the outputs  -> u16 [H][W][D], disparity maps */
+    SVA_STAGE_SGM = 3,       /* K2 then K3 (WTA / LR / sub-pixel): S and the outputs -> u16 [H][W][D], disparity maps */
     SVA_STAGE_ALL = 100
 } sva_stage;
 
@@ -203,7 +203,7 @@ int sva_frame_mark_ad_ready(sva_ctx* ctx);
 int sva_frame_download_ad(sva_ctx* ctx, uint16_t* out);         /* [H][W][D] */
 int sva_frame_download_cost(sva_ctx* ctx, uint16_t* out);       /* [H][W][D] */
 int sva_frame_download_raw_cost(sva_ctx* ctx, uint32_t* out);   /* RAW_U32 recomputed from A: [H][W][D] */
-int sva_frame_download_sgm(sva_ctx* ctx, uint16_t* out);        /* S [H][W][D] (sum of the first n_paths-1 paths) */
+int sva_frame_download_sgm(sva_ctx* ctx, uint16_t* out);        /* S [H][W][D]: the sum of all n_paths paths (or of the debug direction mask) */
 int sva_frame_download_disparity(sva_ctx* ctx, uint16_t* out_disp, float* out_subpix);
 /* Device pointer + byte size of the A volume, so a caller can reduce it across GPUs (NCCL via torch.distributed). */
 int sva_frame_ad_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);
@@ -215,7 +215,10 @@ int sva_frame_ad_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);
  * (sva_frame_sgm_directions: the result is that rank's partial S over `rows_alloc` >= H rows, rows beyond H zero), reduce-scatters the
  * partial sums by row blocks and runs K3 per block (sva_frame_wta_rows; the left-right check is row-local). */
 int sva_frame_cost_device_ptr(sva_ctx* ctx, void** out_ptr, size_t* out_bytes);  /* C [H][W][D] of the current parameters */
-int sva_frame_set_params(sva_ctx* ctx, const sva_params* p);                      /* same images and mask, new disparity range / SGM parameters */
+/* Same images and mask, new parameters.  The views were staged at upload for that upload's pairs and disparity reach: SVA_STAGE_AD runs
+ * again only if pairs, min_disp and win_half are unchanged and num_disp does not reach further (else SVA_ERR_STATE: upload again); any
+ * parameter set may be used for the stages after K1a (the full range after a disparity-slice cost volume). */
+int sva_frame_set_params(sva_ctx* ctx, const sva_params* p);
 /* dir_mask bit i = direction i of {v+, v-, h+, h-, d++, d-+, d+-, d--}; slice_disp = D/G for a slice-major volume, 0 for [H][W][D] */
 int sva_frame_sgm_directions(sva_ctx* ctx, const void* cost_dev, int32_t slice_disp, uint32_t dir_mask, int32_t rows_alloc, void** out_s_ptr,
                              size_t* out_bytes);

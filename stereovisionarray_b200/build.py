@@ -10,7 +10,7 @@ OBJ = os.path.join(HERE, "csrc", "_obj")
 LIB = os.path.join(HERE, "libsva_b200.so")
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC,-ffp-contract=off",
-         "-fmad=false", "--use_fast_math=false" if False else "-prec-div=true"]
+         "-fmad=false", "-prec-div=true"]
 
 
 def sources():
@@ -26,7 +26,7 @@ def _stale(out, deps):
 
 def _compile(src, verbose):
     obj = os.path.join(OBJ, src[:-3] + ".o")
-    deps = [os.path.join(CSRC, src), os.path.join(CSRC, "sva_common.cuh"), os.path.join(CSRC, "sva_vec.cuh"), os.path.join(HERE, "..", "include", "sva_c_api.h")]
+    deps = [os.path.join(CSRC, src), os.path.join(HERE, "..", "include", "sva_c_api.h")] + [os.path.join(CSRC, h) for h in os.listdir(CSRC) if h.endswith(".cuh")]
     if not _stale(obj, deps):
         return obj, ""
     cmd = [NVCC] + FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-c", os.path.join(CSRC, src), "-o", obj]

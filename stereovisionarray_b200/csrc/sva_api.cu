@@ -44,21 +44,37 @@ static int check_image(sva_ctx* c, const sva_image_u8* im, int W, int H, const c
     return SVA_OK;
 }
 
-extern "C" {
+// rows [b0, b1) join the interval [a0, a1) a volume already holds of this frame when they touch it, and replace it otherwise
+static void merge_rows(int& a0, int& a1, int b0, int b1) {
+    if (a1 <= a0 || b0 > a1 || b1 < a0) { a0 = b0; a1 = b1; return; }
+    a0 = std::min(a0, b0); a1 = std::max(a1, b1);
+}
 
-int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask) {
-    if (!c) return SVA_ERR_BAD_ARG;
-    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+static int check_frame_args(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask) {
     SVA_TRY(check_params(c, p));
     const int W = p->width, H = p->height;
     SVA_TRY(check_image(c, ref, W, H, "ref"));
     if (!others) return c->fail(SVA_ERR_BAD_ARG, "null others");
     for (int i = 0; i < p->n_pairs; i++) SVA_TRY(check_image(c, &others[i], W, H, "other view"));
     if (mask) SVA_TRY(check_image(c, mask, W, H, "mask"));
+    return SVA_OK;
+}
+
+extern "C" {
+
+int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    SVA_TRY(check_frame_args(c, p, ref, others, mask));
+    const int W = p->width, H = p->height;
     c->prm = *p;
+    c->up_prm = *p;  // the view staging (zero borders, phi column offsets, line images) is laid out for THIS disparity reach and these pairs
+    c->ad_params_ok = true;
     c->win_y0 = 0; c->win_rows = 0;
     c->pair_begin = 0; c->pair_end = p->n_pairs;
     c->have_frame = c->have_ad = c->have_cost = c->have_sgm = c->have_disp = false;
+    c->s_prezeroed = false;
+    c->ad_y0 = c->ad_y1 = c->cost_y0 = c->cost_y1 = 0;
     const size_t img = (size_t)W * H;
     c->use_ad2 = sva_ad2_usable(*p) && !c->tune_ad_gather;
     if (c->use_ad2) {
@@ -121,22 +137,42 @@ static int prezero_s(sva_ctx* c) {
 
 static int run_stage(sva_ctx* c, int stage) {
     switch (stage) {
-        case SVA_STAGE_AD:
+        case SVA_STAGE_AD: {
             if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
-            return c->use_ad2 ? sva_run_ad2(c) : sva_run_ad(c);
-        case SVA_STAGE_BOX:
+            if (!c->ad_params_ok)
+                return c->fail(SVA_ERR_STATE, "sva_frame_set_params changed the pairs / disparity reach the views were staged for at upload: upload the frame again before SVA_STAGE_AD");
+            SVA_TRY(c->use_ad2 ? sva_run_ad2(c) : sva_run_ad(c));
+            // rows of A that now hold this frame: the block's rows +- win_half (clipped), or everything
+            const int H = c->prm.height, k = c->prm.win_half;
+            if (c->pair_begin != 0 || c->pair_end != c->prm.n_pairs) c->ad_y0 = c->ad_y1 = 0;  // a pair-range partial replaces what A held
+            merge_rows(c->ad_y0, c->ad_y1, c->win_rows > 0 ? std::max(0, c->win_y0 - k) : 0, c->win_rows > 0 ? std::min(H, c->win_y0 + c->win_rows + k) : H);
+            return SVA_OK;
+        }
+        case SVA_STAGE_BOX: {
             if (!c->have_ad) return c->fail(SVA_ERR_STATE, "AD volume not computed");
-            return sva_run_box(c, false);
+            const int H = c->prm.height, k = c->prm.win_half;
+            const int y0 = c->win_rows > 0 ? c->win_y0 : 0, y1 = c->win_rows > 0 ? c->win_y0 + c->win_rows : H;
+            if (c->ad_y1 > c->ad_y0 && (std::max(0, y0 - k) < c->ad_y0 || std::min(H, y1 + k) > c->ad_y1))  // (an externally reduced A has no interval: ad_y0 == ad_y1)
+                return c->fail(SVA_ERR_STATE, "the AD volume does not cover the rows this box filter reads: run SVA_STAGE_AD for the current row block");
+            SVA_TRY(sva_run_box(c, false));
+            merge_rows(c->cost_y0, c->cost_y1, y0, y1);
+            return SVA_OK;
+        }
         case SVA_STAGE_SGM:
             if (!c->have_cost) return c->fail(SVA_ERR_STATE, "cost volume not computed");
             if (c->win_rows > 0)  // only the block's rows of the cost volume exist
                 return c->fail(SVA_ERR_STATE, "a row block is active (sva_frame_rows_begin): use sva_frame_sgm_rows, or upload the frame again for a whole-frame run");
+            if (c->cost_y0 > 0 || c->cost_y1 < c->prm.height)
+                return c->fail(SVA_ERR_STATE, "the cost volume holds only a row block of this frame: run SVA_STAGE_AD / SVA_STAGE_BOX on the whole frame first");
             return sva_run_sgm(c);
-        case SVA_STAGE_ALL:
+        case SVA_STAGE_ALL: {
             SVA_TRY(prezero_s(c));
-            SVA_TRY(run_stage(c, SVA_STAGE_AD));
-            SVA_TRY(run_stage(c, SVA_STAGE_BOX));
-            return run_stage(c, SVA_STAGE_SGM);
+            int rc = run_stage(c, SVA_STAGE_AD);
+            if (rc == SVA_OK) rc = run_stage(c, SVA_STAGE_BOX);
+            if (rc == SVA_OK) rc = run_stage(c, SVA_STAGE_SGM);
+            if (rc != SVA_OK) c->s_prezeroed = false;  // nobody will join ev_zero for this run
+            return rc;
+        }
         default: return c->fail(SVA_ERR_BAD_ARG, "unknown stage");
     }
 }
@@ -279,6 +315,7 @@ int sva_frame_ad_device_ptr(sva_ctx* c, void** out_ptr, size_t* out_bytes) {
 int sva_frame_mark_ad_ready(sva_ctx* c) {
     if (!c || !c->have_frame) return SVA_ERR_BAD_ARG;
     c->have_ad = true;
+    c->ad_y0 = c->ad_y1 = 0;  // written by the caller: no interval to check
     return SVA_OK;
 }
 
@@ -307,6 +344,15 @@ int sva_frame_set_params(sva_ctx* c, const sva_params* p) {
     if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
     SVA_TRY(check_params(c, p));
     if (p->width != c->prm.width || p->height != c->prm.height) return c->fail(SVA_ERR_BAD_ARG, "set_params cannot change the image size");
+    // K1a reads the views through the staging built at upload (zero borders sized for the upload's disparity reach, per-view column phase
+    // phi = gx * min_disp mod 4, line-image pitch): it may only run again for the same pairs, the same min_disp and no further reach.
+    // Other parameter sets (e.g. the full range after a disparity-slice cost volume, for SGM / WTA) are accepted, but SVA_STAGE_AD then
+    // needs a new upload.
+    const sva_params& u = c->up_prm;
+    bool same = p->n_pairs == u.n_pairs && p->min_disp == u.min_disp && p->win_half == u.win_half && (p->num_disp + 31) / 32 <= (u.num_disp + 31) / 32;
+    for (int i = 0; same && i < p->n_pairs; i++) same = p->pair_gx[i] == u.pair_gx[i] && p->pair_gy[i] == u.pair_gy[i];
+    c->ad_params_ok = same;
+    c->ad_y0 = c->ad_y1 = c->cost_y0 = c->cost_y1 = 0;
     c->prm = *p;
     c->win_y0 = 0; c->win_rows = 0;
     c->pair_begin = 0; c->pair_end = p->n_pairs;
@@ -337,12 +383,14 @@ int sva_frame_rows_begin(sva_ctx* c, int32_t y0, int32_t rows) {
     c->s_prezeroed = false;
     c->have_sgm = false;
     c->win_y0 = y0; c->win_rows = rows == p.height ? 0 : rows;  // SVA_STAGE_AD / SVA_STAGE_BOX now compute what this block needs
+    // (the volumes keep what they hold: [ad_y0, ad_y1) / [cost_y0, cost_y1) say which rows, and every consumer checks its rows against them)
     return SVA_OK;
 }
 
 int sva_frame_sgm_rows(sva_ctx* c, int32_t group, int32_t y0, int32_t rows, const void* state_in, void* state_out) {
     if (!c) return SVA_ERR_BAD_ARG;
     if (!c->have_cost) return c->fail(SVA_ERR_STATE, "sgm_rows: no cost volume");
+    if (y0 < c->cost_y0 || y0 + rows > c->cost_y1) return c->fail(SVA_ERR_STATE, "sgm_rows: the cost volume was not computed for these rows");
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
     SVA_TRY(sva_run_sgm_rows(c, group, y0, rows, (const uint16_t*)state_in, (uint16_t*)state_out));
     c->have_sgm = true;
@@ -410,13 +458,14 @@ int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, 
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->d2h_stream));
     }
+    SVA_TRY(check_frame_args(c, p, ref, others, mask));  // a bad frame must not disturb the frames in flight: nothing is touched before this
     if (t >= 2) SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[slot]));  // frame t-2 is out: its IoSet is free again
     swap_io(c);
     cudaStream_t compute = c->stream;
     c->stream = c->h2d_stream;
     int rc = sva_frame_upload(c, p, ref, others, mask);
     c->stream = compute;
-    SVA_TRY(rc);
+    if (rc != SVA_OK) { swap_io(c); return rc; }  // (allocation failure): back onto the IoSet of frame t-1, the ticket is not consumed
     SVA_CUDA_OK(c, cudaEventRecord(c->ev_h2d[slot], c->h2d_stream));
     SVA_CUDA_OK(c, cudaStreamWaitEvent(compute, c->ev_h2d[slot], 0));
     SVA_TRY(run_stage(c, SVA_STAGE_ALL));

@@ -85,6 +85,9 @@ struct sva_ctx {
     // ---- resident frame state (volume mode) ----
     bool have_frame = false, have_ad = false, have_cost = false, have_sgm = false, have_disp = false;
     sva_params prm{};
+    sva_params up_prm{};        // parameters of the last upload: what the view staging was laid out for
+    bool ad_params_ok = false;  // prm still matches that staging (sva_frame_set_params may break it; SVA_STAGE_AD then refuses)
+    int ad_y0 = 0, ad_y1 = 0, cost_y0 = 0, cost_y1 = 0;  // image rows of A / C that hold the current frame (row-block runs fill only part)
     int pair_begin = 0, pair_end = 0;
     bool has_mask = false;
     bool debug_store_full_s = false;

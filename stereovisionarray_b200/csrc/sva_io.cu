@@ -115,6 +115,7 @@ int sva_yaml_read_matrix(const char* path, const char* name, void* out, int64_t 
     if (!data) return SVA_ERR_BAD_ARG;
     long r = 0, cc = 0;
     if (!field_int(node, data, "rows", r) || !field_int(node, data, "cols", cc) || r < 0 || cc < 0) return SVA_ERR_BAD_ARG;
+    if (r > INT32_MAX || cc > INT32_MAX) return SVA_ERR_BAD_ARG;  // untrusted input: the shape must survive the int32 outputs ...
     const char* dt = std::strstr(node, "dt:");
     if (!dt || dt >= data) return SVA_ERR_BAD_ARG;
     dt = skip_ws(dt + 3);
@@ -123,8 +124,8 @@ int sva_yaml_read_matrix(const char* path, const char* name, void* out, int64_t 
     if (*dt == 'u') type = 0; else if (*dt == 'd') type = 1; else return SVA_ERR_BAD_ARG;  // single-channel u8 / f64 only
     *rows = (int32_t)r; *cols = (int32_t)cc; *dtype = type;
     if (!out) return SVA_OK;
-    const size_t n = (size_t)r * cc, esz = type == 0 ? 1 : 8;
-    if ((int64_t)(n * esz) > cap_bytes) return SVA_ERR_BAD_ARG;
+    const size_t n = (size_t)r * cc, esz = type == 0 ? 1 : 8;  // ... so n < 2^62 and the product below cannot wrap past the check
+    if (cap_bytes < 0 || n > (size_t)INT64_MAX / 8 || (int64_t)(n * esz) > cap_bytes) return SVA_ERR_BAD_ARG;
     const char* p = std::strchr(data, '[');
     if (!p) return SVA_ERR_BAD_ARG;
     p++;
@@ -142,7 +143,8 @@ int sva_yaml_read_matrix(const char* path, const char* name, void* out, int64_t 
             if (e == p) return SVA_ERR_BAD_ARG;
             p = e;
         }
-        if (type == 0) ((uint8_t*)out)[i] = (uint8_t)v; else ((double*)out)[i] = v;
+        if (type == 0) ((uint8_t*)out)[i] = (uint8_t)(v >= 0.0 && v <= 255.0 ? v : (v > 255.0 ? 255.0 : 0.0));  // NaN / out of range: defined, clamped
+        else ((double*)out)[i] = v;
     }
     return SVA_OK;
 }

@@ -100,8 +100,10 @@ def slice_params(p, rank, world):
 
 
 def slice_sharded_compute(ctx, p, rank, world, group=None, keep=None):
-    """Device part of slice_sharded_depth for a frame that is already uploaded on every rank (with any disparity range of the same
-    images): steps 1-5 below; afterwards the rank's rows of the maps are in the library (ctx.download_disparity_rows).  Returns (y0, y1)."""
+    """Device part of slice_sharded_depth for a frame that is already uploaded on every rank WITH THE RANK'S SLICE PARAMETERS
+    (slice_params(p, rank, world): the view staging is laid out for the upload's disparity reach, and the library refuses to run K1a for
+    any other — sva_frame_set_params): steps 1-5 below; afterwards the rank's rows of the maps are in the library
+    (ctx.download_disparity_rows).  Returns (y0, y1)."""
     import torch
     import torch.distributed as dist
     from . import abi

@@ -55,16 +55,19 @@ def ellipse_mask(h, w):
     return np.where(e < 1, 255, 0).astype(np.uint8)
 
 
-def render_view(ref, disp, gx, gy, fill):
-    """forward-warp ref into the camera at grid offset (gx, gy); nearer (larger delta) wins; holes <- fill."""
+def render_view(ref, disp, gx, gy, fill, order=None):
+    """forward-warp ref into the camera at grid offset (gx, gy); nearer (larger delta) wins; holes <- fill.
+    One scatter in ascending-disparity order (numpy keeps the LAST value written to a repeated index), i.e. far first, near overwrites;
+    `order` = np.argsort(disp.ravel(), kind="stable"), shared by the views of a scene."""
     h, w = ref.shape
     out = fill.copy()
-    yy, xx = np.mgrid[0:h, 0:w]
-    for lv in np.unique(disp):  # ascending: far first, near overwrites
-        m = disp == lv
-        ty, tx = yy[m] - gy * lv, xx[m] - gx * lv
-        ok = (ty >= 0) & (ty < h) & (tx >= 0) & (tx < w)
-        out[ty[ok], tx[ok]] = ref[m][ok]
+    if order is None:
+        order = np.argsort(disp.ravel(), kind="stable")
+    lv = disp.ravel()[order]
+    ty = order // w - gy * lv
+    tx = order % w - gx * lv
+    ok = (ty >= 0) & (ty < h) & (tx >= 0) & (tx < w)
+    out[ty[ok], tx[ok]] = ref.ravel()[order[ok]]
     return out
 
 
@@ -72,7 +75,8 @@ def make_scene(h, w, num_disp, offsets, seed, min_disp=0, face=False):
     """returns dict(ref, others[list], gt[int32 disparity], mask[u8 or None])."""
     ref = texture(h, w, seed)
     gt = gt_disparity(h, w, num_disp, min_disp, face=face, seed=seed)
-    others = [render_view(ref, gt, gx, gy, texture(h, w, seed + 1 + k)) for k, (gx, gy) in enumerate(offsets)]
+    order = np.argsort(gt.ravel(), kind="stable")
+    others = [render_view(ref, gt, gx, gy, texture(h, w, seed + 1 + k), order) for k, (gx, gy) in enumerate(offsets)]
     return {"ref": ref, "others": others, "gt": gt, "mask": ellipse_mask(h, w) if face else None}
 
 

@@ -239,3 +239,58 @@ def test_row_block_pipeline_emulated_on_one_gpu(ctx, h, w, D, blocks):
         assert np.array_equal(d, d_full[y0:y1]) and np.array_equal(s, s_full[y0:y1])
     assert blk.check_guards()[1] == 0
     blk.close()
+
+
+def test_state_guards_of_the_staged_api(ctx, oracle):
+    """round-1 review findings, each as the sequence that used to go wrong silently:
+    (1) set_params to a further disparity reach than the upload staged the views for, then K1a; (2) a bad frame in the middle of a
+    capture stream; (3) a whole-frame SGM over a cost volume of which only a row block was computed"""
+    from stereovisionarray_b200._lib import SvaError
+    h, w, D = 64, 96, 64
+    sc = synth.make_scene(h, w, D, OFF8, 77)
+    p = abi.make_params(w, h, D, OFF8, win_half=4, n_paths=8, lr_gx=-1)
+    # (1)
+    p_small = abi.make_params(w, h, 32, OFF8, win_half=4, n_paths=8, lr_gx=-1)
+    ctx.upload(p_small, sc["ref"], sc["others"])
+    ctx.set_params(p)  # reaches 32 disparities further than the zero borders of the staged views
+    with pytest.raises(SvaError, match="upload the frame again"):
+        ctx.run(abi.STAGE_AD)
+    ctx.set_params(p_small)  # back inside the staged reach: fine, and exact
+    ctx.run(abi.STAGE_AD)
+    assert np.array_equal(ctx.download_ad(), oracle.ad_volume(p_small, sc["ref"], sc["others"]))
+    p_shift = abi.make_params(w, h, 32, OFF8, win_half=4, n_paths=8, lr_gx=-1, min_disp=1)  # same reach, other column phase
+    ctx.set_params(p_shift)
+    with pytest.raises(SvaError):
+        ctx.run(abi.STAGE_AD)
+    # (2)
+    frames = [synth.make_scene(h, w, D, OFF8, 500 + i) for i in range(4)]
+    outs = [(np.empty((h, w), np.uint16), np.empty((h, w), np.float32)) for _ in frames]
+    keep = [abi.image_array(f["others"]) for f in frames]
+    tickets = []
+    for i, (f, k, o) in enumerate(zip(frames, keep, outs)):
+        if i == 2:
+            with pytest.raises(SvaError):  # wrong image size: refused before anything of the frames in flight is touched
+                ctx.stream_submit(p, f["ref"][:, :50], k, None, o[0], o[1])
+        tickets.append(ctx.stream_submit(p, f["ref"], k, None, o[0], o[1]))
+    assert tickets == list(range(tickets[0], tickets[0] + 4))
+    for t in tickets:
+        ctx.stream_wait(t)
+    for f, o in zip(frames, outs):
+        d_o, s_o = oracle.depth_from_array(p, f["ref"], f["others"])
+        assert np.array_equal(o[0], d_o) and np.array_equal(o[1], s_o)
+    # (3)
+    ctx.upload(p, sc["ref"], sc["others"])
+    ctx.rows_begin(16, 20)
+    ctx.run(abi.STAGE_AD)
+    ctx.run(abi.STAGE_BOX)
+    with pytest.raises(SvaError, match="cost volume was not computed for these rows"):
+        ctx.sgm_rows(2, 0, 16)
+    ctx.rows_begin(0, h)  # "whole frame" again, but C still holds only rows 16..36
+    with pytest.raises(SvaError, match="only a row block"):
+        ctx.run(abi.STAGE_SGM)
+    ctx.run(abi.STAGE_AD)
+    ctx.run(abi.STAGE_BOX)
+    ctx.run(abi.STAGE_SGM)
+    d, s = ctx.download_disparity()
+    d_o, s_o = oracle.depth_from_array(p, sc["ref"], sc["others"])
+    assert np.array_equal(d, d_o) and np.array_equal(s, s_o)
