@@ -35,7 +35,8 @@ typedef enum sva_status {
     SVA_ERR_CUDA = -3,         /* CUDA runtime error; text in sva_last_error() */
     SVA_ERR_NO_DEVICE = -4,    /* no sm_100 device: there is NO CPU fallback */
     SVA_ERR_STATE = -5,        /* stage called before the stage that produces its input */
-    SVA_ERR_NOMEM = -6
+    SVA_ERR_NOMEM = -6,
+    SVA_ERR_COMM = -7          /* multi-GPU: NCCL / CUDA-IPC failure, or a neighbour's hand-off did not arrive in time */
 } sva_status;
 
 /* enum pairType — include/functions.h:8-19, same values in the same order. */
@@ -233,6 +234,53 @@ int sva_frame_download_disparity_rows(sva_ctx* ctx, int32_t rows, uint16_t* out_
  * the caller moves them between GPUs (a few MB per hop).  sva_frame_wta_rows(ctx, NULL, y0, rows) then runs K3 on the block. */
 int sva_frame_rows_begin(sva_ctx* ctx, int32_t y0, int32_t rows);
 int sva_frame_sgm_rows(sva_ctx* ctx, int32_t group, int32_t y0, int32_t rows, const void* state_in, void* state_out);
+
+/* ---- multi-GPU from C: one process per GPU, one context per process and GPU ------------------------------------------
+ * The reference has no counterpart (it is single-threaded); the sharding units are its own loops: the PAIR loop
+ * src/CameraStereoVision.cpp:55 over the pair list of getCameraPairs (include/functions.h:34-36, src/functions.cpp:150-155), and the
+ * pixel-ROW loop src/CameraStereoVision.cpp:49.
+ *
+ * Communicator: NCCL, loaded at run time with dlopen("libnccl.so.2") (the library has no link-time dependency on it).  Rank 0 calls
+ * sva_comm_get_unique_id and hands the 128 bytes to the other ranks by any means (MPI, a file, torch.distributed ...); every rank then
+ * calls sva_comm_init (collective). */
+#define SVA_COMM_ID_BYTES 128
+#define SVA_IPC_HANDLE_BYTES 64
+int sva_comm_get_unique_id(uint8_t out_id[SVA_COMM_ID_BYTES]);
+int sva_comm_init(sva_ctx* ctx, const uint8_t id[SVA_COMM_ID_BYTES], int32_t rank, int32_t world);
+int sva_comm_destroy(sva_ctx* ctx);
+int sva_comm_barrier(sva_ctx* ctx);  /* all ranks' ctx streams meet (one-word all-reduce), then the host waits for its stream */
+/* Pair sharding, the scheme north_star names: after SVA_STAGE_AD over this rank's pair range (sva_frame_set_pair_range) the partial AD
+ * volumes are sum-reduced onto `root` as packed u32 — NCCL has no 16-bit integer type, and a cell's total is <= 255 * 32 < 2^16, so no carry
+ * crosses the half-word: bit-exact in any order.  On root the volume is then complete (as after SVA_STAGE_AD over all pairs). */
+int sva_frame_reduce_ad(sva_ctx* ctx, int32_t root);
+/* The whole pair-sharded frame in one collective call: upload everywhere, K1a over the rank's pairs (balanced contiguous ranges, e.g. 15
+ * pairs over 8 ranks = 2,2,2,2,2,2,2,1), reduce, and on root K1b + SGM + K3 and the download (out_* are ignored elsewhere). */
+int sva_depth_pair_sharded(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask,
+                           int32_t root, uint16_t* out_disp, float* out_subpix);
+
+/* Row-block pipeline with PEER-DIRECT hand-off: rank r owns image rows [r * ceil(H / G), ...), computes their cost volume and
+ * horizontal paths locally, and continues the row-sweeping path lines of its neighbour: the march kernel of the block above (below) stores L
+ * of every line after its last row STRAIGHT INTO THIS rank's state buffer over NVLink (a peer-mapped pointer), a flag kernel publishes the
+ * frame's sequence number, and a wait kernel on this rank's stream holds the next march until it is there — no host in the loop, no NCCL on
+ * the data path.  sva_rows_run only enqueues; several contexts per GPU (each with its own link) keep several frames in flight.
+ *   sva_rows_open      allocates the link memory (two state buffers of 3 * W * D u16 and the flags) for this geometry and rank
+ *   sva_rows_export / sva_rows_connect    CUDA-IPC handle of the link memory out / the neighbours' handles in (NULL at the array's ends)
+ *   sva_rows_connect_comm                 the same exchange over the context's communicator (collective)
+ *   sva_rows_connect_local                neighbours that live in the same process (tests; one process driving several GPUs)
+ *   sva_rows_run       enqueue this rank's part of the uploaded frame (K1a, K1b, horizontal paths, both sweeps, K3 on the block)
+ *   sva_rows_download  wait for it; SVA_ERR_COMM if a hand-off did not arrive within SVA_ROWS_TIMEOUT_MS (default 20000) */
+int sva_rows_open(sva_ctx* ctx, const sva_params* p, int32_t rank, int32_t world);
+int sva_rows_export(sva_ctx* ctx, uint8_t out_handle[SVA_IPC_HANDLE_BYTES]);
+int sva_rows_connect(sva_ctx* ctx, const uint8_t* prev_handle, const uint8_t* next_handle);
+int sva_rows_connect_comm(sva_ctx* ctx);
+int sva_rows_connect_local(sva_ctx* ctx, sva_ctx* prev, sva_ctx* next);
+int sva_rows_block(const sva_ctx* ctx, int32_t* out_y0, int32_t* out_rows);
+int sva_rows_run(sva_ctx* ctx);
+int sva_rows_download(sva_ctx* ctx, uint16_t* out_disp_rows, float* out_subpix_rows);  /* the block's rows; out_subpix_rows may be NULL */
+int sva_rows_close(sva_ctx* ctx);
+/* one synchronous call per frame: upload + sva_rows_run + sva_rows_download */
+int sva_depth_rows_sharded(sva_ctx* ctx, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask,
+                           uint16_t* out_disp_rows, float* out_subpix_rows);
 
 #ifdef __cplusplus
 }

@@ -23,6 +23,9 @@ EXPORTS = [
     "sva_frame_download_disparity", "sva_frame_ad_device_ptr", "sva_frame_mark_ad_ready",
     "sva_frame_cost_device_ptr", "sva_frame_set_params", "sva_frame_sgm_directions", "sva_frame_wta_rows", "sva_frame_download_disparity_rows",
     "sva_frame_rows_begin", "sva_frame_sgm_rows",
+    "sva_comm_get_unique_id", "sva_comm_init", "sva_comm_destroy", "sva_comm_barrier", "sva_frame_reduce_ad", "sva_depth_pair_sharded",
+    "sva_rows_open", "sva_rows_export", "sva_rows_connect", "sva_rows_connect_comm", "sva_rows_connect_local", "sva_rows_block", "sva_rows_run",
+    "sva_rows_download", "sva_rows_close", "sva_depth_rows_sharded",
 ]
 
 _lib = None
@@ -44,6 +47,10 @@ def lib():
         L.sva_last_error.restype = C.c_char_p
         L.sva_last_error.argtypes = [C.c_void_p]
         L.sva_create.argtypes = [C.c_int, C.POINTER(C.c_void_p)]
+        L.sva_rows_connect_local.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.sva_rows_connect.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        for n in ("sva_rows_open", "sva_comm_init"):
+            getattr(L, n).argtypes = [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32]
         missing = [n for n in EXPORTS if not hasattr(L, n)]
         if missing:
             raise ImportError("libsva_b200.so does not export %s — rebuild it" % missing)

@@ -16,6 +16,9 @@ SVA_ERR_CUDA = -3
 SVA_ERR_NO_DEVICE = -4
 SVA_ERR_STATE = -5
 SVA_ERR_NOMEM = -6
+SVA_ERR_COMM = -7
+SVA_COMM_ID_BYTES = 128
+SVA_IPC_HANDLE_BYTES = 64
 
 # enum pairType — reference include/functions.h:8-19
 ORTHOGONAL, DIAGONAL, TO_CENTER, LINE_HORIZONTAL, LINE_VERTICAL, CROSS, JUMP_CROSS, TO_CENTER_SMALL, MID_LEFT, MID_TOP = range(10)

@@ -103,7 +103,11 @@ struct sva_ctx {
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
-    DevBuf pad_imgs, pad_ref;
+    DevBuf pad_imgs, pad_ref, comm_scratch;
+    // ---- multi-GPU (sva_dist.cu) ----
+    void* comm = nullptr;        // ncclComm_t (sva_comm_init)
+    int comm_rank = 0, comm_world = 1;
+    void* rows_link = nullptr;   // RowsLink: peer-mapped state buffers and flags of the row-block pipeline (sva_rows_open)
     Ad2Geom ad2;
     uint64_t ad2_zero_key = 0;
     bool use_ad2 = false;      // this frame's AD volume comes from k_ad_tile (all pair offsets within +-2) instead of the line-image gather

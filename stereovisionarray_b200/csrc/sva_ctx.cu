@@ -8,6 +8,8 @@
 // A guarded allocation is [GUARD_BYTES canary][payload, poisoned][GUARD_BYTES canary]; sva_debug_check_guards counts canary bytes
 // that changed (an out-of-bounds write), and the poison makes a read of never-written memory show up as a parity failure instead of
 // passing on the zeros a fresh cudaMalloc usually returns.
+void sva_dist_release(sva_ctx* c);  // sva_dist.cu: communicator and row-block link
+
 static constexpr size_t GUARD_BYTES = 256 << 10;
 static constexpr int GUARD_CANARY = 0xA5, GUARD_POISON = 0xCD;
 
@@ -24,7 +26,7 @@ void sva_ctx::release(DevBuf& b) {
 }
 
 void sva_ctx::device_bufs(std::vector<DevBuf*>& out) {
-    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf,
+    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf, &comm_scratch,
            &alt.pad_ref, &alt.pad_imgs, &alt.ref_img, &alt.other_imgs, &alt.lines, &alt.mask, &alt.disp, &alt.subpix};
 }
 
@@ -108,6 +110,7 @@ int sva_destroy(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
+    sva_dist_release(c);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(c->d2h_stream); }
     std::vector<DevBuf*> bufs;

@@ -211,11 +211,15 @@ def row_sharded_compute(ctx, p, rank, world, group=None, keep=None, device="cuda
     ctx.rows_begin(y0, n)
     ctx.run(abi.STAGE_AD)
     ctx.run(abi.STAGE_BOX)
-    ctx.sgm_rows(2, y0, n)
+    starts_chain = world > 1 and rank in (0, world - 1)  # these run their (local) horizontal paths after their first block, off the serial chain
+    if not starts_chain:
+        ctx.sgm_rows(2, y0, n)
     if rank == 0:
         ctx.sgm_rows(0, y0, n, 0, d_out.data_ptr())
     if rank == world - 1:
         ctx.sgm_rows(1, y0, n, 0, u_out.data_ptr())
+    if starts_chain:
+        ctx.sgm_rows(2, y0, n)
     for send_d, recv_d, send_u, recv_u in row_pipeline_steps(rank, world):
         ops = []
         if send_d is not None:
@@ -259,6 +263,44 @@ def row_sharded_depth(ctx, p, ref, others, mask, rank, world, group=None, keep=N
     s_t[:y1 - y0] = torch.from_numpy(s)
     if world == 1:
         return d_t[:p.height].numpy().astype(np.uint16), s_t[:p.height].numpy()
+    d_all = [torch.empty_like(d_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    s_all = [torch.empty_like(s_t, device="cuda") for _ in range(world)] if rank == 0 else None
+    dist.gather(d_t.cuda(), d_all, dst=0, group=group)
+    dist.gather(s_t.cuda(), s_all, dst=0, group=group)
+    if rank != 0:
+        return None
+    return torch.cat(d_all)[:p.height].cpu().numpy().astype(np.uint16), torch.cat(s_all)[:p.height].cpu().numpy()
+
+
+def rows_direct_connect(ctx, p, rank, world, group=None):
+    """Open the C library's row-block link on this rank and map the neighbours' state buffers (CUDA IPC): the 64-byte handles travel over
+    torch.distributed as plain bytes (host plumbing; a C++ host would use sva_rows_connect_comm or its own channel).  Collective."""
+    import torch.distributed as dist
+    ctx.rows_open(p, rank, world)
+    if world == 1:
+        return
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.rows_export(), group=group)
+    ctx.rows_connect(handles[rank - 1] if rank > 0 else None, handles[rank + 1] if rank < world - 1 else None)
+    dist.barrier(group=group)  # nobody runs ahead of a neighbour that has not mapped its side yet
+
+
+def rows_direct_depth(ctx, p, ref, others, mask, rank, world, group=None):
+    """One frame through the peer-direct row-block pipeline (sva_rows_*; rows_direct_connect first): the path-line state is stored by the
+    neighbour's march kernel straight into this GPU's memory and sequenced by device flags.  Returns (disp, subpix) on rank 0, None elsewhere."""
+    import torch
+    import torch.distributed as dist
+    from . import abi
+    ctx.upload(p, ref, others, mask)
+    ctx.rows_run()
+    d, s = ctx.rows_download()
+    if world == 1:
+        return d, s
+    rows_per = row_blocks(p.height, world)[0]
+    d_t = torch.full((rows_per, p.width), abi.SVA_DISP_INVALID, dtype=torch.int32)
+    s_t = torch.full((rows_per, p.width), -1.0, dtype=torch.float32)
+    d_t[:d.shape[0]] = torch.from_numpy(d.astype(np.int32))
+    s_t[:d.shape[0]] = torch.from_numpy(s)
     d_all = [torch.empty_like(d_t, device="cuda") for _ in range(world)] if rank == 0 else None
     s_all = [torch.empty_like(s_t, device="cuda") for _ in range(world)] if rank == 0 else None
     dist.gather(d_t.cuda(), d_all, dst=0, group=group)

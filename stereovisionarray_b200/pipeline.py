@@ -182,6 +182,79 @@ class DepthContext:
         check(self._h, self._L.sva_frame_download_disparity_rows(self._h, int(rows), _p(disp, C.c_uint16), _p(sub, C.c_float)))
         return disp, sub
 
+    # ---- multi-GPU from C: NCCL communicator, pair-sharded reduce, row-block pipeline with peer-direct hand-off (csrc/sva_dist.cu) ----
+    @staticmethod
+    def comm_unique_id():
+        """rank 0: the 128-byte NCCL id to hand to every rank (bytes)"""
+        buf = (C.c_uint8 * abi.SVA_COMM_ID_BYTES)()
+        rc = lib().sva_comm_get_unique_id(buf)
+        if rc != 0:
+            raise RuntimeError("sva_comm_get_unique_id failed with %d (libnccl.so.2 not loadable?)" % rc)
+        return bytes(buf)
+
+    def comm_init(self, uid, rank, world):
+        check(self._h, self._L.sva_comm_init(self._h, (C.c_uint8 * abi.SVA_COMM_ID_BYTES).from_buffer_copy(uid), int(rank), int(world)))
+
+    def comm_barrier(self):
+        check(self._h, self._L.sva_comm_barrier(self._h))
+
+    def comm_destroy(self):
+        check(self._h, self._L.sva_comm_destroy(self._h))
+
+    def reduce_ad(self, root=0):
+        check(self._h, self._L.sva_frame_reduce_ad(self._h, int(root)))
+
+    def depth_pair_sharded(self, p, ref, others, mask=None, root=0):
+        """collective; returns (disp, subpix) on root and None elsewhere"""
+        r, rk = abi.image_u8(ref)
+        o, ok = abi.image_array(others) if not isinstance(others, tuple) else others
+        m = None
+        if mask is not None:
+            m, mk = abi.image_u8(mask)
+        disp = np.empty((p.height, p.width), np.uint16)
+        sub = np.empty((p.height, p.width), np.float32)
+        check(self._h, self._L.sva_depth_pair_sharded(self._h, C.byref(p), C.byref(r), o, C.byref(m) if m is not None else None, int(root),
+                                                       _p(disp, C.c_uint16), _p(sub, C.c_float)))
+        self.params = p
+        return disp, sub
+
+    def rows_open(self, p, rank, world):
+        check(self._h, self._L.sva_rows_open(self._h, C.byref(p), int(rank), int(world)))
+
+    def rows_export(self):
+        buf = (C.c_uint8 * abi.SVA_IPC_HANDLE_BYTES)()
+        check(self._h, self._L.sva_rows_export(self._h, buf))
+        return bytes(buf)
+
+    def rows_connect(self, prev_handle, next_handle):
+        mk = lambda h: (C.c_uint8 * abi.SVA_IPC_HANDLE_BYTES).from_buffer_copy(h) if h is not None else None
+        check(self._h, self._L.sva_rows_connect(self._h, mk(prev_handle), mk(next_handle)))
+
+    def rows_connect_comm(self):
+        check(self._h, self._L.sva_rows_connect_comm(self._h))
+
+    def rows_connect_local(self, prev_ctx, next_ctx):
+        check(self._h, self._L.sva_rows_connect_local(self._h, prev_ctx._h if prev_ctx is not None else None, next_ctx._h if next_ctx is not None else None))
+
+    def rows_block(self):
+        y0, n = C.c_int32(), C.c_int32()
+        check(self._h, self._L.sva_rows_block(self._h, C.byref(y0), C.byref(n)))
+        return y0.value, n.value
+
+    def rows_run(self):
+        """enqueue this rank's block of the uploaded frame (asynchronous)"""
+        check(self._h, self._L.sva_rows_run(self._h))
+
+    def rows_download(self):
+        y0, n = self.rows_block()
+        disp = np.empty((n, self.params.width), np.uint16)
+        sub = np.empty((n, self.params.width), np.float32)
+        check(self._h, self._L.sva_rows_download(self._h, _p(disp, C.c_uint16), _p(sub, C.c_float)))
+        return disp, sub
+
+    def rows_close(self):
+        check(self._h, self._L.sva_rows_close(self._h))
+
     # ---- one call, host in / host out (the e2e path) ----
     def depth_from_array(self, p, ref, others, mask=None, disp=None, sub=None):
         r, rk = abi.image_u8(ref)
