@@ -73,50 +73,125 @@ class ClockSampler:
         return out
 
 
-def algorithmic_bytes(name, p, n_cam, launches_per_step=1.0):
-    """per launch, DESIGN.md §4: s_C = s_S = 2 bytes"""
+def split_label(label):
+    """timing label of the library: '<kernel symbol as ncu prints it>/<what the launch carries>' (plain symbol for the other kernels)"""
+    sym, _, what = label.partition("/")
+    return sym, what
+
+
+def schedule_bytes(label, p, n_cam):
+    """Minimum DRAM bytes ONE launch of this kernel has to move in the schedule the library runs (s_C = s_S = 2 bytes per cell):
+    what `roofline.achieved` is computed from.  A launch that carries several row-sweeping SGM directions streams C once and
+    read-modify-writes S once for all of them (they share the lines in L2): 6 B/DE; the two horizontal directions cannot share: 12 B/DE."""
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
-    if name in ("k_ad_planar", "k_ad_tile"):
-        return n_cam * px + 2 * de
-    if name in ("k_box_cost", "k_box_planar"):
-        return 4 * de
-    if name.startswith("k_sgm_store"):
-        return 4 * de
-    if name == "k_sgm_red_multi":  # bytes per launch: the frame's 6P - 4 ~ 6P bytes per cell spread over its launches
-        return 6 * de * p.n_paths / max(1.0, launches_per_step)  # every direction streams C once and read-modify-writes S once
-    if name == "k_wta_tile":
-        return 2 * de + 6 * px
-    if name == "k_wta_seg":
-        return 2 * de + 6 * px   # S once, winner map + the other view's key map
-    if name == "k_wta_finish":
-        return 18 * px           # winner, key, mask, three S cells, u16 + f32 outputs
-    if name == "k_lr_check":
+    sym, what = split_label(label)
+    if sym in ("k_ad_planar", "k_ad_tile"):
+        return n_cam * px + 2 * de          # views in, A out
+    if sym in ("k_box_cost", "k_box_planar"):
+        return 4 * de                       # A in, C out
+    if sym.startswith("k_sgm_acc"):
+        n = int(what[-1]) if what and what[-1].isdigit() else 1
+        if what.startswith("store_"):
+            return 4 * de * n
+        if "horizontal" in what or "mixed" in what:
+            return 6 * de * n               # every direction streams C and read-modify-writes S on its own
+        return 6 * de                       # row-sweeping directions of one launch share C and S (each ranged launch streams them once)
+    if sym.startswith("k_wta_seg") or sym.startswith("k_wta_tile"):
+        return 2 * de + 6 * px              # S once, winner map + the other view's key map
+    if sym.startswith("k_wta_finish"):
+        return 18 * px                      # winner, key, mask, three S cells, u16 + f32 outputs
+    if sym.startswith("k_lr_check"):
         return 10 * px
-    if name.startswith("k_sgm_red"):
-        return 6 * de
     return None
+
+
+def textbook_bytes(label, p, n_cam):
+    """SURVEY §8(d)'s per-path count for the same launch: every SGM direction streams C once and read-modify-writes S once (6 B/DE each)"""
+    de = p.width * p.height * p.num_disp
+    sym, what = split_label(label)
+    if sym.startswith("k_sgm_acc") and not what.startswith("store_"):
+        n = int(what[-1]) if what and what[-1].isdigit() else 1
+        return 6 * de * n
+    return schedule_bytes(label, p, n_cam)
+
+
+def load_traffic(key, order):
+    """profiles/traffic.json (tools/traffic_from_ncu.py): ncu records of the launches of one frame of THIS configuration, paired with
+    the library's own launch list of a frame (`order`: timing labels in launch order) -> {label: averaged record}; {} without a capture"""
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            recs = json.load(f).get(key, {}).get("launches", [])
+    except Exception:
+        return {}
+    norm = lambda s: s.replace(" ", "")
+    if len(recs) != len(order) or any(norm(split_label(l)[0]) not in norm(r["kernel"]) for l, r in zip(order, recs)):
+        return {}  # the capture is of another build / schedule: refuse rather than print stale numbers
+    out = {}
+    for l, r in zip(order, recs):
+        out.setdefault(l, []).append(r)
+    avg = {}
+    for l, rs in out.items():
+        a = {"dram_bytes": sum(r["dram_bytes"] for r in rs) / len(rs), "bound": max(set(r["bound"] for r in rs), key=[r["bound"] for r in rs].count)}
+        for k in ("hbm_pct", "l1tex_pct", "alu_pct", "lsu_pct", "issue_pct", "warps_pct"):
+            v = [r[k] for r in rs if r.get(k) is not None]
+            a[k] = round(sum(v) / len(v), 1) if v else None
+        avg[l] = a
+    return avg
 
 
 def dist_env():
     return int(os.environ.get("RANK", "0")), int(os.environ.get("LOCAL_RANK", "0")), int(os.environ.get("WORLD_SIZE", "1"))
 
 
+class Ranks:
+    """barrier / max-over-ranks plumbing (torch.distributed over NCCL when launched by torchrun)"""
+
+    def __init__(self):
+        import torch
+        self.torch = torch
+        self.rank, self.local_rank, self.world = dist_env()
+        self.dist = None
+        if self.world > 1:
+            import torch.distributed as dist
+            torch.cuda.set_device(self.local_rank)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", self.local_rank))
+            self.dist = dist
+
+    def barrier(self):
+        if self.dist:
+            self.dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max(self, v):
+        if not self.dist:
+            return v
+        t = self.torch.tensor([v], dtype=self.torch.float64, device="cuda")
+        self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def close(self):
+        if self.dist:
+            self.dist.destroy_process_group()
+
+
 def run_sva(args):
     import torch
-    rank, local_rank, world = dist_env()
-    use_dist = world > 1
-    if use_dist:
-        import torch.distributed as dist
-        torch.cuda.set_device(local_rank)
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    R = Ranks()
+    rank, local_rank, world = R.rank, R.local_rank, R.world
     from stereovisionarray_b200.pipeline import DepthContext
     name = args.config
+    if name == "literal":
+        return run_literal(args, R)
     cfg = configs.CONFIGS[name]
     p = configs.params(name, win_half=args.win_half)
     n_cam = p.n_pairs + 1
     if name == "c3":
-        return run_pair_sharded(args, rank, local_rank, world)
+        out = run_c3(args, R, headline=True)
+        if rank == 0:
+            emit(json.dumps(out))
+        R.close()
+        return
     # capture batch: c4 has 64 frames per step split over the ranks (strong scaling); the others one frame per rank per step (weak)
     from stereovisionarray_b200 import dist as sdist
     batch = cfg["frames"]
@@ -126,30 +201,19 @@ def run_sva(args):
     sc = configs.scene(name, frame=fb)  # every rank works on its own frames of the capture batch
     ctx = DepthContext(local_rank)
 
-    def barrier():
-        if use_dist:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    def max_over_ranks(v):
-        if not use_dist:
-            return v
-        t = torch.tensor([v], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item())
-
     # ---- resident: inputs already in HBM ----
     ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
     for _ in range(args.warmup):
         ctx.run(abi.STAGE_ALL)
     ctx.synchronize()
+    order = [n for n, _ in ctx.kernel_times(abi.STAGE_ALL)]  # the launches of one frame, in order
     l0 = ctx.launches()
     sampler = ClockSampler(local_rank) if rank == 0 else None
-    barrier()
+    R.barrier()
     total_ms, kern = ctx.time_detailed(abi.STAGE_ALL, args.steps * frames_rank)
-    barrier()
+    R.barrier()
     launches = ctx.launches() - l0
-    total_ms = max_over_ranks(total_ms)
+    total_ms = R.max(total_ms)
     mde = configs.mde_per_frame(name)
     value = frames_step_total * mde * args.steps / (total_ms / 1e3)
 
@@ -168,7 +232,7 @@ def run_sva(args):
     # (a) one synchronous call per frame: upload, kernels and download back to back
     for _ in range(max(1, args.warmup)):
         ctx.depth_from_array(p, ref_h, others_c, mask_h, disp_h, sub_h)
-    barrier()
+    R.barrier()
     ctx.timer_start()
     for _ in range(args.steps * frames_rank):
         ctx.depth_from_array(p, ref_h, others_c, mask_h, disp_h, sub_h)
@@ -177,181 +241,371 @@ def run_sva(args):
     # t-1's download overlap frame t's kernels.  Timed on the device from the first upload to the end of the last download.
     for i in range(max(2, args.warmup)):
         ctx.stream_wait(ctx.stream_submit(p, ref_h, others_c, mask_h, outs[i % 2][2], outs[i % 2][3]))
-    barrier()
+    R.barrier()
     ctx.stream_mark()
     last = None
     for i in range(args.steps * frames_rank):
         last = ctx.stream_submit(p, ref_h, others_c, mask_h, outs[i % 2][2], outs[i % 2][3])
     e2e_ms = ctx.stream_elapsed(last)
-    barrier()
+    R.barrier()
     clocks = sampler.stop() if sampler else None
-    e2e_ms = max_over_ranks(e2e_ms)
-    single_ms = max_over_ranks(single_ms)
+    e2e_ms = R.max(e2e_ms)
+    single_ms = R.max(single_ms)
     e2e_value = frames_step_total * mde * args.steps / (e2e_ms / 1e3)
     h2d = frames_rank * (n_cam * p.width * p.height + (p.width * p.height if mask_h is not None else 0))
     d2h = frames_rank * p.width * p.height * (2 + 4)
+    ctx.close()
 
-    if rank != 0:
-        if use_dist:
-            dist.destroy_process_group()
-        return
-    # ---- roofline of the dominant kernel + the per-kernel table ----
-    peak, peak_src = measured_peak()
-    traffic = {}
+    out = None
+    if rank == 0:
+        # ---- roofline of the dominant kernel + the per-kernel table ----
+        peak, peak_src = measured_peak()
+        traffic = load_traffic("%s_k%d" % (name, args.win_half), order)
+        de = p.width * p.height * p.num_disp
+        rows = []
+        for kname, (sum_ms, cnt) in kern.items():
+            sb, tb = schedule_bytes(kname, p, n_cam), textbook_bytes(kname, p, n_cam)
+            avg_ms = sum_ms / max(1, cnt)
+            sym, what = split_label(kname)
+            tr = traffic.get(kname)
+            rows.append({"kernel": sym, "launch": what or None, "launches_per_step": cnt / args.steps / frames_rank, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
+                         "schedule_bytes": sb, "achieved_gbs": round(sb / avg_ms / 1e6, 1) if sb else None, "frac": round(sb / avg_ms / 1e6 / peak, 4) if sb else None,
+                         "frac_textbook": round(tb / avg_ms / 1e6 / peak, 4) if tb else None,
+                         "traffic": int(tr["dram_bytes"]) if tr else None, "dram_frac": round(tr["dram_bytes"] / avg_ms / 1e6 / peak, 4) if tr else None,
+                         "bound": tr["bound"] if tr else None, "ncu_pct": {k[:-4]: tr[k] for k in ("hbm_pct", "l1tex_pct", "alu_pct", "lsu_pct", "issue_pct", "warps_pct")} if tr else None})
+        rows.sort(key=lambda r: -r["share"])
+        dom = next(r for r in rows if r["schedule_bytes"])
+        per_frame = lambda pred: sum(s for k, (s, c) in kern.items() if pred(split_label(k)[0])) / args.steps / frames_rank
+        sgm_ms = per_frame(lambda s: s.startswith("k_sgm"))
+        sgm_sched = sum(schedule_bytes(k, p, n_cam) * c for k, (s, c) in kern.items() if split_label(k)[0].startswith("k_sgm")) / args.steps / frames_rank
+        sgm_text = (6 * p.n_paths - 4) * de if p.n_paths else 0
+        k1_ms = per_frame(lambda s: s.startswith("k_ad") or s.startswith("k_box"))
+        k1_bytes = n_cam * p.width * p.height + 2 * de  # the views in, the packed cost volume out (A is an implementation detail)
+        stage = lambda b, ms: {"bytes": int(b), "ms": round(ms, 4), "achieved_gbs": round(b / ms / 1e6, 1) if ms else None, "frac": round(b / ms / 1e6 / peak, 4) if ms else None}
+        roofline = {"bound": ("hbm" if dom["bound"] in (None, "hbm") else dom["bound"]) if dom["traffic"] else "hbm",
+                    "bound_source": "ncu capture of this configuration (profiles/traffic.json)" if dom["traffic"] else "assumed: no ncu capture of this configuration and build in profiles/traffic.json",
+                    "kernel": dom["kernel"], "launch": dom["launch"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
+                    "frac_definition": "schedule bytes (DESIGN.md §4: what this launch must move given which directions share C and S in L2) / event-timed launch / measured HBM peak",
+                    "frac_textbook": dom["frac_textbook"], "frac_of_8000": round(dom["achieved_gbs"] / 8000.0, 4),
+                    "traffic": dom["traffic"], "dram_frac": dom["dram_frac"], "peak_source": peak_src,
+                    "sgm_stage": dict(stage(sgm_sched, sgm_ms), textbook_bytes=int(sgm_text), frac_textbook=round(sgm_text / sgm_ms / 1e6 / peak, 4) if sgm_ms else None),
+                    "cost_volume_stage": dict(stage(k1_bytes, k1_ms), note="K1a + K1b against SURVEY §8(d)'s N_cam*H*W + 2*H*W*D; bound by the integer pipe / L1TEX, not by HBM (DESIGN.md §4)")}
+        out = {
+            "metric": "MDE/s", "value": round(value, 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if batch > 1 else "weak", "vs_baseline": None, "dtype": "u16",
+            "data": "synthetic", "frames_per_s": round(frames_step_total * args.steps / (total_ms / 1e3), 2),
+            "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": n_cam,
+                       "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths, "frames_per_step_per_gpu": frames_rank,
+                       "partitioning": "independent frames per GPU, no data-path collective" if world > 1 else "single GPU",
+                       "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
+            "e2e": {"value": round(e2e_value, 1), "unit": "MDE/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "api": "sva_stream_submit / sva_stream_wait (C ABI, pinned host buffers, two frames in flight: a THROUGHPUT figure)",
+                    "single_call_ms_per_step": round(single_ms / args.steps, 4), "single_call_api": "sva_depth_from_array, one synchronous call per frame (the latency a one-frame user sees)"},
+            "gpu_launches": int(launches), "roofline": roofline, "clocks": clocks, "kernels": rows,
+        }
+        # ---- CPU baselines (rank 0, N = 1): bounded samples on the box's host cores ----
+        if world == 1 and not args.no_cpu:
+            out["cpu_baseline"] = cpu_baseline_legs(args, name, p)
+            try:
+                out["literal_mode"] = literal_mode_line(p.width, p.height)
+            except Exception as ex:  # reported, never fatal for the headline line
+                out["literal_mode"] = {"error": str(ex)[:200]}
+        else:
+            out["cpu_baseline"] = None
+    # ---- the multi-GPU configurations north_star names, on the same ranks: extra keys of the same line ----
+    if not args.no_extras:
+        with Watchdog(args.extras_timeout, rank, out):
+            ex = {}
+            for key, fn in (("c4_strong", run_c4_strong), ("c3", run_c3)):
+                try:
+                    ex[key] = fn(args, R)
+                except Exception as e:  # noqa: BLE001 — reported in the line
+                    ex[key] = {"error": "%s: %s" % (type(e).__name__, str(e)[:300])}
+            if out is not None:
+                out.update(ex)
+    if rank == 0:
+        emit(json.dumps(out))
+    R.close()
+
+
+class Watchdog:
+    """the extra configurations must never cost the headline line: after `seconds` rank 0 prints the line it has and every rank exits"""
+
+    def __init__(self, seconds, rank, out):
+        import threading
+        self.t = threading.Timer(seconds, self.fire)
+        self.t.daemon = True
+        self.rank, self.out, self.seconds = rank, out, seconds
+
+    def fire(self):
+        if self.rank == 0 and self.out is not None:
+            self.out["extras_error"] = "the multi-GPU extras did not finish within %d s" % self.seconds
+            emit(json.dumps(self.out))
+        os._exit(0)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.t.cancel()
+        return False
+
+
+def cpu_baseline_legs(args, name, p):
+    """BASELINE.md §4 on the GPU box's host cores, each a bounded sample: CPU-fast (the parity oracle's OpenMP volume pipeline — the headline
+    `value`, same unit as the GPU line), CPU-ref-1T and CPU-ref-MT (the reference's algorithm restated: per-candidate brute-force 40x40 SAD
+    over Bresenham candidates, one thread as the reference runs, and OpenMP over rows), in the reference arm's unit."""
+    from oracle.oracle import Oracle
+    orc = Oracle()
+    band = min(p.height, args.cpu_band)
+    scb = configs.scene(name, frame=0, height=band)
+    pb = abi.make_params(p.width, band, p.num_disp, configs.offsets(name), win_half=args.win_half, n_paths=p.n_paths, lr_gx=-1, subpixel=1)
+    orc.depth_from_array(pb, scb["ref"], scb["others"], scb["mask"])  # warm-up
+    best = 1e30
+    for _ in range(3):
+        t0 = time.perf_counter()
+        orc.depth_from_array(pb, scb["ref"], scb["others"], scb["mask"])
+        best = min(best, time.perf_counter() - t0)
+    cpu = {"value": round(p.width * band * p.num_disp / 1e6 / best, 2), "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port",
+           "sample": "CPU-fast: oracle/sva_oracle.c volume pipeline (OpenMP) on a %dx%d row band of the %s frame, D=%d, %d pairs, best of 3" % (p.width, band, name, p.num_disp, p.n_pairs)}
     try:
-        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
-            traffic = json.load(f).get("%s_k%d" % (name, args.win_half), {})
-    except Exception:
-        pass
-    rows = []
-    for kname, (sum_ms, cnt) in kern.items():
-        ab = algorithmic_bytes(kname, p, n_cam, cnt / args.steps / frames_rank)
-        avg_ms = sum_ms / max(1, cnt)
-        rows.append({"kernel": kname, "launches_per_step": cnt / args.steps / frames_rank, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
-                     "algorithmic_bytes": ab, "achieved_gbs": round(ab / avg_ms / 1e6, 1) if ab else None,
-                     "frac": round(ab / avg_ms / 1e6 / peak, 4) if ab else None, "traffic": traffic.get(kname)})
-    rows.sort(key=lambda r: -r["share"])
-    dom = next(r for r in rows if r["algorithmic_bytes"])
-    sgm_ms = sum(s for k, (s, c) in kern.items() if k.startswith("k_sgm")) / args.steps / frames_rank
-    sgm_bytes = (6 * p.n_paths - 4) * p.width * p.height * p.num_disp if p.n_paths else 0
-    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                "traffic": dom["traffic"], "peak_source": peak_src, "frac_of_8000": round(dom["achieved_gbs"] / 8000.0, 4),
-                # actual DRAM bytes (ncu) / event-timed duration: below `achieved` when L2 sharing moves fewer bytes than the algorithmic count
-                "dram_gbs": round(dom["traffic"] / dom["avg_ms"] / 1e6, 1) if dom["traffic"] else None,
-                "dram_frac": round(dom["traffic"] / dom["avg_ms"] / 1e6 / peak, 4) if dom["traffic"] else None,
-                "sgm_stage": {"algorithmic_bytes": sgm_bytes, "ms": round(sgm_ms, 4), "achieved_gbs": round(sgm_bytes / sgm_ms / 1e6, 1) if sgm_ms else None,
-                              "frac": round(sgm_bytes / sgm_ms / 1e6 / peak, 4) if sgm_ms else None}}
-    # ---- CPU baseline (rank 0, N = 1): the oracle port of the SAME pipeline on a bounded row band, all host cores ----
-    cpu = None
-    if world == 1 and not args.no_cpu:
-        from oracle.oracle import Oracle
-        orc = Oracle()
-        band = min(p.height, args.cpu_band)
-        scb = configs.scene(name, frame=0, height=band)
-        pb = abi.make_params(p.width, band, p.num_disp, configs.offsets(name), win_half=args.win_half, n_paths=p.n_paths, lr_gx=-1, subpixel=1)
-        orc.depth_from_array(pb, scb["ref"], scb["others"], scb["mask"])  # warm-up
-        best = 1e30
+        w, rows = p.width, 64
+        lit = synth.make_literal_scene(rows, w, 7000)
+        cams = [abi.camera(*c) for c in synth.reference_cameras(w)]
+        mask = np.zeros((rows, w), np.uint8)
+        mask[20:rows - 20, 20:w - 20] = 255
+        ev = literal_evals(w, rows)
+        legs = {}
+        for key, nt in (("ref_1t", 1), ("ref_mt", orc.num_threads())):
+            best = 1e30
+            for _ in range(2):
+                t0 = time.perf_counter()
+                orc.match_literal(lit["images"], cams, [(12, 11)], mask, 20, 0.5, 1.0, n_threads=nt)
+                best = min(best, time.perf_counter() - t0)
+            legs[key] = {"value": round(ev / 1e6 / best, 3), "unit": "MDE/s (pixel x candidate evaluations)", "cores": nt, "seconds": round(best, 3)}
+        cpu["reference_algorithm"] = dict(legs, sample="oracle restatement of src/CameraStereoVision.cpp:49-95 on a %dx%d band, pair {12,11}, best of 2; "
+                                          "full-frame time = linear extrapolation by rows (x %.1f)" % (w, rows, (p.height - 40) / (rows - 40)))
+    except Exception as ex:  # noqa: BLE001
+        cpu["reference_algorithm"] = {"error": str(ex)[:200]}
+    return cpu
+
+
+def run_c4_strong(args, R):
+    """c4 (64 frames x 1920x1080, 9 cameras, D = 192): the frames of the batch partitioned over the ranks, no data-path collective.
+    Strong scaling: `ms_per_step` is the whole 64-frame batch."""
+    from stereovisionarray_b200 import dist as sdist
+    from stereovisionarray_b200.pipeline import DepthContext
+    name = "c4"
+    p = configs.params(name, win_half=args.win_half)
+    batch = configs.CONFIGS[name]["frames"]
+    fb, fe = sdist.frame_range(batch, R.world, R.rank)
+    sc = configs.scene(name, frame=fb)
+    ctx = DepthContext(R.local_rank)
+    try:
+        ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
         for _ in range(3):
-            t0 = time.perf_counter()
-            orc.depth_from_array(pb, scb["ref"], scb["others"], scb["mask"])
-            best = min(best, time.perf_counter() - t0)
-        cpu = {"value": round(p.width * band * p.num_disp / 1e6 / best, 2), "unit": "MDE/s", "cores": orc.num_threads(), "kind": "port",
-               "sample": "oracle/sva_oracle.c volume pipeline (OpenMP) on a %dx%d row band of the %s frame, D=%d, %d pairs, best of 3" % (p.width, band, name, p.num_disp, p.n_pairs)}
-    literal = None
-    if world == 1 and not args.no_cpu:
-        try:
-            literal = literal_mode_line(p.width, p.height)
-        except Exception as ex:  # reported, never fatal for the headline line
-            literal = {"error": str(ex)[:200]}
-    out = {
-        "metric": "MDE/s", "value": round(value, 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(total_ms / args.steps, 4), "higher_is_better": True, "scaling": "strong" if batch > 1 else "weak", "vs_baseline": None, "dtype": "u16",
-        "data": "synthetic", "frames_per_s": round(frames_step_total * args.steps / (total_ms / 1e3), 2),
-        "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": n_cam,
-                   "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths, "frames_per_step_per_gpu": frames_rank,
-                   "partitioning": "independent frames per GPU, no data-path collective" if world > 1 else "single GPU",
-                   "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
-        "e2e": {"value": round(e2e_value, 1), "unit": "MDE/s", "ms_per_step": round(e2e_ms / args.steps, 4), "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                "api": "sva_stream_submit / sva_stream_wait (C ABI, pinned host buffers, two frames in flight)",
-                "single_call_ms_per_step": round(single_ms / args.steps, 4), "single_call_api": "sva_depth_from_array, one synchronous call per frame"},
-        "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "literal_mode": literal, "clocks": clocks, "kernels": rows,
-    }
-    emit(json.dumps(out))
-    if use_dist:
-        dist.destroy_process_group()
+            ctx.run(abi.STAGE_ALL)
+        ctx.synchronize()
+        steps = 2
+        R.barrier()
+        ms = ctx.time(abi.STAGE_ALL, steps * (fe - fb))
+        R.barrier()
+        ms = R.max(ms) / steps
+    finally:
+        ctx.close()
+    return {"workload": "c4: " + configs.CONFIGS[name]["desc"], "scaling": "strong", "n_gpus": R.world, "frames_per_step": batch, "frames_per_gpu": fe - fb,
+            "ms_per_step": round(ms, 3), "frames_per_s": round(batch / (ms / 1e3), 2), "value": round(batch * configs.mde_per_frame(name) / (ms / 1e3), 1), "unit": "MDE/s",
+            "steps": steps, "timing": "CUDA events on the library's stream, inputs resident, max over ranks"}
 
 
-def run_pair_sharded(args, rank, local_rank, world):
-    """c3: ONE frame per step; the camera pairs are split over the ranks, the packed AD partials are sum-reduced (NCCL) onto rank 0,
-    which runs the box filter, SGM and WTA.  Strong scaling.  Timed with CUDA events on torch's current stream (the library is told
-    to run on that stream so its kernels and the NCCL reduce are ordered)."""
-    import torch
-    import torch.distributed as dist
+def run_c3(args, R, headline=False):
+    """c3 (one 3840x2160x256 frame, 16 cameras): on one GPU the whole frame; on several the row-block pipeline with peer-direct hand-off
+    (sva_rows_*: no volume ever crosses GPUs, the path-line state of the row-sweeping directions is stored straight into the next GPU's
+    memory).  Two figures: the latency of one frame with all ranks starting together, and frames back to back with `in_flight` contexts per
+    GPU (the sweeps of consecutive frames fill each other's pipeline bubbles)."""
     from stereovisionarray_b200 import dist as sdist
     from stereovisionarray_b200.pipeline import DepthContext
     name = "c3"
     cfg = configs.CONFIGS[name]
     p = configs.params(name, win_half=args.win_half)
     sc = configs.scene(name, frame=0)
-    torch.cuda.set_device(local_rank)
-    ctx = DepthContext(local_rank)
+    mde = configs.mde_per_frame(name)
+    world, rank = R.world, R.rank
+    steps = max(2, min(args.steps, 5))
+    base = {"workload": "c3: " + cfg["desc"], "scaling": "strong", "n_gpus": world, "unit": "MDE/s", "steps": steps,
+            "timing": "CUDA events on the library's streams, inputs resident, max over ranks"}
+    if world == 1:
+        ctx = DepthContext(R.local_rank)
+        try:
+            ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+            for _ in range(2):
+                ctx.run(abi.STAGE_ALL)
+            ctx.synchronize()
+            l0 = ctx.launches()
+            ms = ctx.time(abi.STAGE_ALL, steps) / steps
+            launches = ctx.launches() - l0
+        finally:
+            ctx.close()
+        res = dict(base, scheme="single GPU: the whole frame, no exchange", latency_ms=round(ms, 3), ms_per_frame=round(ms, 3), frames_per_s=round(1e3 / ms, 2),
+                   value=round(mde / (ms / 1e3), 1))
+    elif headline and args.c3_scheme != "rows_direct":
+        res = dict(base, **run_c3_host_sequenced(args, R, p, sc, steps))
+        launches = res.pop("launches")
+    else:
+        in_flight = 3
+        ctxs = [DepthContext(R.local_rank) for _ in range(in_flight)]
+        try:
+            for c in ctxs:
+                c.upload(p, sc["ref"], sc["others"], sc["mask"])
+                sdist.rows_direct_connect(c, p, rank, world)
+            for c in ctxs:  # warm-up: allocates every workspace
+                c.rows_run()
+            for c in ctxs:
+                c.rows_download()
+            l0 = ctxs[0].launches()
+            lat = 0.0
+            for _ in range(steps):  # latency: one frame, all ranks start together
+                R.barrier()
+                ctxs[0].timer_start()
+                ctxs[0].rows_run()
+                lat += R.max(ctxs[0].timer_stop())
+                ctxs[0].rows_download()  # checks the hand-off time-outs
+            lat /= steps
+            launches = (ctxs[0].launches() - l0) // steps
+            frames = 4 * in_flight
+            R.barrier()
+            for c in ctxs:
+                c.timer_start()
+            for i in range(frames):
+                ctxs[i % in_flight].rows_run()
+            thr = R.max(max(c.timer_stop() for c in ctxs)) / frames
+            for c in ctxs:
+                c.rows_download()
+            R.barrier()
+        finally:
+            for c in ctxs:
+                c.close()
+        blocks = sdist.row_blocks(p.height, world)[1]
+        res = dict(base, scheme="row blocks %s end to end (sva_rows_*): cost volume and horizontal paths local, row-sweeping paths continue across GPUs — each march stores "
+                                "%.1f MB of path state straight into the next GPU's memory (CUDA IPC over NVLink), sequenced by device flags; no volume collective, no NCCL on the data path"
+                                % (blocks, 3 * p.width * p.num_disp * 2 / 1e6),
+                   latency_ms=round(lat, 3), latency_value=round(mde / (lat / 1e3), 1), in_flight=in_flight, ms_per_frame=round(thr, 3), frames_per_s=round(1e3 / thr, 2),
+                   value=round(mde / (thr / 1e3), 1), parity="tools/check_sharded.py --c3: bit-exact against the oracle digests (profiles/)")
+    if not headline:
+        return res
+    # `--config c3` as the headline: the contract's keys, value = frames back to back
+    peak, peak_src = measured_peak()
+    return {"metric": "MDE/s", "value": res["value"], "unit": "MDE/s", "n_gpus": world, "steps": steps, "warmup": args.warmup, "ms_per_step": res["ms_per_frame"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "frames_per_s": res["frames_per_s"],
+            "config": {"workload": res["workload"], "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": p.n_pairs + 1, "pairs": p.n_pairs, "win_half": p.win_half,
+                       "sgm_paths": p.n_paths, "partitioning": res["scheme"], "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
+            "c3": res, "e2e": None, "gpu_launches": int(launches), "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "note": "see the c1 line for per-kernel rooflines"},
+            "cpu_baseline": None}
+
+
+def run_c3_host_sequenced(args, R, p, sc, steps):
+    """the schemes whose exchange steps are NCCL collectives issued from Python (kept for comparison): 'pairs' = north_star's pair
+    sharding + packed reduce of the AD volume onto rank 0; 'slices' = disparity slices / directions / row blocks; 'rows' = the row-block pipeline
+    with NCCL send / recv hops.  Timed with CUDA events on torch's current stream, which the library is told to run on."""
+    import torch
+    import torch.distributed as dist
+    from stereovisionarray_b200 import dist as sdist
+    from stereovisionarray_b200.pipeline import DepthContext
+    rank, world = R.rank, R.world
+    ctx = DepthContext(R.local_rank)
     stream = torch.cuda.current_stream()
     ctx.set_stream(stream.cuda_stream)
+    scheme, keep = args.c3_scheme, {}
     b, e = sdist.pair_ranges(p.n_pairs, world)[rank]
-    slices = args.c3_scheme == "slices" and world > 1  # one GPU: nothing to exchange, the frame runs as one plain pipeline
-    rows = args.c3_scheme == "rows" and world > 1
-    keep = {}
-    if slices:
-        ctx.upload(sdist.slice_params(p, rank, world), sc["ref"], sc["others"], sc["mask"])
-    elif rows:
-        ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
-    else:
-        ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+    ctx.upload(sdist.slice_params(p, rank, world) if scheme == "slices" else p, sc["ref"], sc["others"], sc["mask"])
+    if scheme == "pairs":
         ptr, nbytes = ctx.ad_device_ptr()
         vol = torch.as_tensor(sdist._CudaAlias(ptr, nbytes // 4), device="cuda")
 
     def step():
-        if slices:
+        if scheme == "slices":
             sdist.slice_sharded_compute(ctx, p, rank, world, None, keep)
-            return
-        if rows:
+        elif scheme == "rows":
             sdist.row_sharded_compute(ctx, p, rank, world, None, keep)
-            return
-        if e > b:
-            ctx.set_pair_range(b, e)
-            ctx.run(abi.STAGE_AD)
         else:
-            vol.zero_()
-        if world > 1:
+            if e > b:
+                ctx.set_pair_range(b, e)
+                ctx.run(abi.STAGE_AD)
+            else:
+                vol.zero_()
             dist.reduce(vol, dst=0, op=dist.ReduceOp.SUM)
-        if rank == 0:
-            ctx.mark_ad_ready()
-            ctx.run(abi.STAGE_BOX)
-            ctx.run(abi.STAGE_SGM)
+            if rank == 0:
+                ctx.mark_ad_ready()
+                ctx.run(abi.STAGE_BOX)
+                ctx.run(abi.STAGE_SGM)
+    try:
+        for _ in range(2):
+            step()
+        l0 = ctx.launches()
+        R.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record(stream)
+        for _ in range(steps):
+            step()
+        e1.record(stream)
+        R.barrier()
+        ms = R.max(e0.elapsed_time(e1)) / steps
+        launches = (ctx.launches() - l0) // steps
+    finally:
+        ctx.close()
+    mde = configs.mde_per_frame("c3")
+    return {"scheme": "%s (host-sequenced NCCL exchange; see DESIGN.md §7)" % scheme, "latency_ms": round(ms, 3), "ms_per_frame": round(ms, 3), "frames_per_s": round(1e3 / ms, 2),
+            "value": round(mde / (ms / 1e3), 1), "launches": launches}
 
+
+def run_literal(args, R):
+    """`--config literal`: the REFERENCE'S OWN algorithm (src/CameraStereoVision.cpp:49-95 + improveWithDisparity) on the GPU, in the
+    reference arm's unit and on its frame size, so that this line and `--impl reference --config literal` are like for like:
+    MDE = pixel x candidate evaluations of pair {12,11} on a 1280-wide frame."""
+    import ctypes as C
+    from stereovisionarray_b200 import reference_api as api
+    from stereovisionarray_b200._lib import lib
+    w, h = configs.CONFIGS["c1"]["width"], configs.CONFIGS["c1"]["height"]
+    sc = synth.make_literal_scene(h, w, 7000)
+    cams = [api.Camera(f, pos, ps) for pos, f, ps in synth.reference_cameras(w)]
+    mask = np.zeros((h, w), np.uint8)
+    mask[20:h - 20, 20:w - 20] = 255
+    hnd = api._context(R.local_rank)
+    L = lib()
+
+    def step():
+        return api.improveWithDisparity(api.matchLiteral(sc["images"], cams, [(12, 11)], mask, 20, 0.5, 1.0), sc["images"][12], [sc["images"][11]], [(cams[12], cams[11])], 21, mask)
     for _ in range(args.warmup):
         step()
-    torch.cuda.synchronize()
-    l0 = ctx.launches()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
-    if world > 1:
-        dist.barrier()
-    torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
+    n0 = C.c_uint64(); L.sva_kernel_launches(hnd, C.byref(n0))
+    sampler = ClockSampler(R.local_rank) if R.rank == 0 else None
+    R.barrier()
+    L.sva_timer_start(hnd)
+    t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
-    e1.record(stream)
-    torch.cuda.synchronize()
-    if world > 1:
-        dist.barrier()
-    ms = e0.elapsed_time(e1)
-    if world > 1:
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = float(t.item())
+    wall = time.perf_counter() - t0
+    ms = C.c_float(); L.sva_timer_stop(hnd, C.byref(ms))
+    R.barrier()
     clocks = sampler.stop() if sampler else None
-    launches = ctx.launches() - l0
-    if rank == 0:
-        mde = configs.mde_per_frame(name)
+    n1 = C.c_uint64(); L.sva_kernel_launches(hnd, C.byref(n1))
+    dev_ms, wall_ms = R.max(ms.value), R.max(wall * 1e3)
+    ev = literal_evals(w, h, stride=64) / 1e6
+    if R.rank == 0:
         peak, peak_src = measured_peak()
-        out = {"metric": "MDE/s", "value": round(mde * args.steps / (ms / 1e3), 1), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-               "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u16", "data": "synthetic",
-               "frames_per_s": round(args.steps / (ms / 1e3), 3),
-               "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": p.width, "height": p.height, "num_disp": p.num_disp, "cameras": p.n_pairs + 1,
-                          "pairs": p.n_pairs, "win_half": p.win_half, "sgm_paths": p.n_paths,
-                          "partitioning": ("disparity slices of %d (cost volume, no reduction) -> all-gather -> path directions %s -> reduce-scatter by row blocks -> "
-                                           "row-sharded WTA; %d ranks" % (p.num_disp // world, sdist.direction_masks(p.n_paths, world), world)) if slices else
-                                          ("row blocks %s end to end: cost volume and horizontal paths local, row-sweeping paths as a pipeline handing %.1f MB of path state per hop; no volume collective"
-                                           % (sdist.row_blocks(p.height, world)[1], 3 * p.width * p.num_disp * 2 / 1e6)) if rows else
-                                          ("single GPU: the whole frame, no exchange" if world == 1 else
-                                           "pairs %s over %d ranks; packed-int32 NCCL reduce of the AD volume (%.2f GB) onto rank 0" % (sdist.pair_ranges(p.n_pairs, world), world, nbytes / 1e9)),
-                          "l2": "no flush: each volume (%.0f MB) exceeds the 126 MB L2" % (p.width * p.height * p.num_disp * 2 / 1e6)},
-               "e2e": None, "gpu_launches": int(launches), "roofline": {"bound": "hbm", "peak": peak, "peak_source": peak_src, "note": "see the c1 line for per-kernel rooflines"},
+        out = {"metric": "MDE/s", "value": round(R.world * ev * args.steps / (dev_ms / 1e3), 1), "unit": "MDE/s", "n_gpus": R.world, "steps": args.steps, "warmup": args.warmup,
+               "ms_per_step": round(dev_ms / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
+               "config": {"workload": "literal: the reference driver's loop nest (SAD 40x40 over Bresenham candidates, first-min WTA) + improveWithDisparity, pair {12,11}",
+                          "width": w, "height": h, "mde_definition": "pixel x candidate evaluations, as --impl reference", "mde_per_frame": round(ev, 2),
+                          "value_timing": "CUDA events on the library's stream around the host-buffer calls (the copies are on that stream too: this API has no resident form)"},
+               "e2e": {"value": round(R.world * ev * args.steps / (wall_ms / 1e3), 1), "unit": "MDE/s", "ms_per_step": round(wall_ms / args.steps, 4),
+                       "h2d_bytes_per_step": 4 * w * h + 4 * w * h, "d2h_bytes_per_step": 2 * w * h,
+                       "api": "sva_match_literal + sva_improve_with_disparity (host buffers in and out, wall clock around the calls)"},
+               "gpu_launches": int(n1.value - n0.value), "roofline": {"bound": "alu", "peak": peak, "peak_source": peak_src, "note": "plane SAD + raw box sums per candidate offset: integer-pipe bound, see DESIGN.md §2"},
                "cpu_baseline": None, "clocks": clocks}
         emit(json.dumps(out))
-    if world > 1:
-        dist.destroy_process_group()
+    R.close()
 
 
 def _ref_band_worker(job):
@@ -423,7 +677,7 @@ def run_reference(args):
         return
     from oracle.oracle import Reference
     name = args.config
-    cfg = configs.CONFIGS[name]
+    cfg = configs.CONFIGS["c1" if name == "literal" else name]
     if not Reference.available():
         emit(json.dumps({"impl": "reference", "unavailable": "oracle/_ref/libsva_ref.so missing (built only where /root/reference exists)"}))
         return
@@ -441,10 +695,14 @@ def run_reference(args):
     tot_e = sum(e for _, e in times)
     v = tot_e / 1e6 / tot_t
     sample = ("UNMODIFIED reference main() (oracle/_ref): SAD 40x40 + first-min WTA + improveWithDisparity on %d independent %dx%d bands per step "
-              "(one per core; the reference is single-threaded and has no multi-pair sum / SGM), pair {12,11}, MDE = pixel x candidate evaluations" % (cores, w, band))
+              "(one per core; the reference is single-threaded and has no multi-pair sum / SGM), pair {12,11}, MDE = pixel x candidate evaluations.  "
+              "Like for like with `bench.py --config literal` (the same algorithm on the GPU, same unit and frame width), NOT with the default c1 line (8-pair volume + 8-path SGM, "
+              "array-level cells).  Caveat: compiled against oracle/cvshim, whose Mat expression path allocates and zero-fills a temporary per getAbsDiff call (~1.6 us per 40x40 SAD); "
+              "a real OpenCV 4.2 build is likely 2-4x faster" % (cores, w, band))
     out = {"impl": "reference", "metric": "MDE/s", "value": round(v, 3), "unit": "MDE/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": round(1e3 * tot_t / max(1, len(times)), 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u8", "data": "synthetic",
-           "config": {"workload": "%s: %s" % (name, cfg["desc"]), "width": w, "band_rows": band},
+           "config": {"workload": ("literal: the reference driver's loop nest (SAD 40x40 over Bresenham candidates, first-min WTA) + improveWithDisparity, pair {12,11}" if name == "literal"
+                                   else "%s: %s" % (name, cfg["desc"])), "width": w, "band_rows": band, "mde_definition": "pixel x candidate evaluations"},
            "cpu_baseline": {"value": round(v, 3), "unit": "MDE/s", "cores": cores, "kind": "reference", "sample": sample},
            "e2e": {"value": round(v, 3), "unit": "MDE/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}, "gpu_launches": 0}
     emit(json.dumps(out))
@@ -481,15 +739,18 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--config", default="c1", choices=sorted(configs.CONFIGS))
+    ap.add_argument("--config", default="c1", choices=sorted(configs.CONFIGS) + ["literal"],
+                    help="c0..c4 = BASELINE.json's configurations (volume pipeline); literal = the reference's own algorithm, like for like with --impl reference")
     ap.add_argument("--win-half", type=int, default=20)
     ap.add_argument("--impl", default="sva", choices=["sva", "reference"])
     ap.add_argument("--cpu-band", type=int, default=256, help="rows of the CPU-baseline sample")
     ap.add_argument("--ref-band", type=int, default=44, help="rows per band of the reference arm (40 + valid rows)")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--c3-scheme", default="rows", choices=["pairs", "slices", "rows"],
-                    help="c3 only: 'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding; "
-                         "'rows' = row blocks end to end, row-sweeping paths as a pipeline between neighbours (DESIGN.md §7)")
+    ap.add_argument("--c3-scheme", default="rows_direct", choices=["pairs", "slices", "rows", "rows_direct"],
+                    help="--config c3 only: 'rows_direct' (default) = row blocks end to end with peer-direct hand-off (sva_rows_*); 'rows' = the same pipeline with NCCL send/recv hops; "
+                         "'pairs' = north_star's pair sharding + NCCL reduce of the AD volume; 'slices' = disparity-slice / direction / row sharding (DESIGN.md §7)")
+    ap.add_argument("--no-extras", action="store_true", help="skip the c4-strong and c3 runs that the default line carries as extra keys")
+    ap.add_argument("--extras-timeout", type=int, default=420, help="seconds after which the line is printed without the extras")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "sva" else args.warmup
     with StdoutToStderr():

@@ -2,7 +2,15 @@
 #include <algorithm>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>  // header-only: ranges are no-ops unless a profiler injects itself
+
 #include "sva_common.cuh"
+
+// one NVTX range per pipeline stage: nsys / ncu --nvtx group the kernels by the stage that launched them
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+};
 
 int sva_build_line_images(sva_ctx* ctx);
 int sva_run_ad(sva_ctx* ctx);
@@ -64,6 +72,7 @@ extern "C" {
 
 int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, const sva_image_u8* mask) {
     if (!c) return SVA_ERR_BAD_ARG;
+    NvtxRange range("sva:upload");
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
     SVA_TRY(check_frame_args(c, p, ref, others, mask));
     const int W = p->width, H = p->height;
@@ -136,6 +145,7 @@ static int prezero_s(sva_ctx* c) {
 }
 
 static int run_stage(sva_ctx* c, int stage) {
+    NvtxRange range(stage == SVA_STAGE_AD ? "sva:K1a_ad_volume" : stage == SVA_STAGE_BOX ? "sva:K1b_box_cost" : stage == SVA_STAGE_SGM ? "sva:K2_sgm+K3_wta" : "sva:frame");
     switch (stage) {
         case SVA_STAGE_AD: {
             if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");

@@ -10,6 +10,8 @@
 #include <cstdlib>
 #include <cstring>
 
+#include <nvtx3/nvToolsExt.h>
+
 #include "sva_common.cuh"
 
 // ---- NCCL through dlopen: the few entry points used, declared here so that neither nccl.h nor libnccl is needed to build or load the library ----
@@ -343,6 +345,8 @@ int sva_rows_run(sva_ctx* c) {
     const int r = l->rank, G = l->world;
     if ((r > 0 && !l->prev) || (r < G - 1 && !l->next)) return c->fail(SVA_ERR_STATE, "rows_run: neighbours not connected (sva_rows_connect*)");
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
+    nvtxRangePushA("sva:rows_block");
+    struct Pop { ~Pop() { nvtxRangePop(); } } pop;
     const uint32_t seq = ++l->seq;
     const int y0 = l->y0, n = l->rows;
     uint32_t* err = l->flag(l->mem, F_ERR);

@@ -18,7 +18,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OFF8 = [(-1, -1), (0, -1), (1, -1), (-1, 0), (1, 0), (-1, 1), (0, 1), (1, 1)]
 
 
-@pytest.mark.parametrize("h,w,D,G,offs,k", [(67, 96, 64, 3, OFF8, 4), (90, 140, 128, 4, OFF8, 5), (64, 70, 256, 2, OFF8, 6), (58, 3840, 192, 2, OFF8[:3], 4), (41, 200, 64, 8, OFF8, 3)])
+@pytest.mark.parametrize("h,w,D,G,offs,k", [(67, 96, 64, 3, OFF8, 4), (90, 140, 128, 4, OFF8, 5), (64, 70, 256, 2, OFF8, 6), (58, 3840, 192, 2, OFF8[:3], 4), (43, 200, 64, 8, OFF8, 3)])
 def test_rows_direct_pipeline_with_local_ranks(oracle, h, w, D, G, offs, k):
     """G contexts of this process play the ranks: every rank's march stores its path-line state straight into the next context's link
     memory and the flag kernels sequence the hops; three frames go through the same links (the flags count frames), the first two without
