@@ -37,12 +37,28 @@ class SvaError(RuntimeError):
         self.code = code
 
 
+def _preload_nccl():
+    """The library binds NCCL at run time (dlopen("libnccl.so.2"), csrc/sva_dist.cu).  A process that imports torch AFTERWARDS would find
+    the system's NCCL already mapped under that SONAME instead of the newer copy torch is built against, and fail to import.  So the copy
+    torch bundles (site-packages/nvidia/nccl/lib) is mapped first when it exists; without it the library falls back to the system's."""
+    import sys
+    for base in sys.path:
+        cand = os.path.join(base, "nvidia", "nccl", "lib", "libnccl.so.2")
+        if os.path.exists(cand):
+            try:
+                C.CDLL(cand, mode=C.RTLD_GLOBAL)
+            except OSError:
+                pass
+            return
+
+
 def lib():
     global _lib
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise ImportError("libsva_b200.so is not built (run `python -m stereovisionarray_b200.build` or __graft_entry__.build()); "
                               "there is no CPU fallback for the depth path")
+        _preload_nccl()
         L = C.CDLL(LIB_PATH)
         L.sva_last_error.restype = C.c_char_p
         L.sva_last_error.argtypes = [C.c_void_p]

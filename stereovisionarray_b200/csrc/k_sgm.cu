@@ -119,12 +119,13 @@ int sva_run_wta(sva_ctx* ctx, const uint16_t* vol);
 //               before the async proxy, and the elected lane issues one cp.reduce.async.bulk (.add.u32 — packed u16x2 sums are carry-free by
 //               DESIGN.md §3.3) of the whole cell into S.  The ring has PF + 2 stages: the slot consumed at step s is refilled at step
 //               s + 2, after a bulk wait_group.read has confirmed that the reduce issued from it has read it.
-template <int PF, bool BULK> __host__ __device__ constexpr int sgm_ns() { return BULK ? PF + 2 : PF + 1; }
-template <int NR, int PF, bool BULK> __host__ __device__ constexpr int sgm_warp_smem() {  // bytes per warp: the ring (+ one mbarrier per stage)
+// BULK as a template argument: 0 = per-lane form, 1 = bulk loads of C with per-lane REDs into S, 2 = bulk loads and bulk reduces.
+template <int PF, int BULK> __host__ __device__ constexpr int sgm_ns() { return BULK == 2 ? PF + 2 : PF + 1; }
+template <int NR, int PF, int BULK> __host__ __device__ constexpr int sgm_warp_smem() {  // bytes per warp: the ring (+ one mbarrier per stage)
     return sgm_ns<PF, BULK>() * 32 * 2 * NR * 2 + (BULK ? ((sgm_ns<PF, BULK>() * 8 + 15) & ~15) : 0);
 }
 
-template <int NR, int PF, bool FULL, bool STORE, int BL, bool BULK>
+template <int NR, int PF, bool FULL, bool STORE, int BL, int BULK>
 struct SgmPipe {
     static constexpr int NS = sgm_ns<PF, BULK>(), NV = 2 * NR, STAGE = 32 * NV * 2;
     using V = typename VecSel<NR, BL>::type;
@@ -143,7 +144,7 @@ struct SgmPipe {
         // slice-major cost volume (per-lane form only): a lane's cells never straddle a slice (c_ds % NV == 0)
         const size_t lane_c = q.c_ds > 0 ? (size_t)(le / q.c_ds) * q.H * q.W * q.c_ds + le % q.c_ds : (size_t)le;
         C = BULK ? q.C : q.C + lane_c;
-        S = BULK ? q.S : q.S + le;
+        S = BULK == 2 ? q.S : q.S + le;
         ring = warp_base + lane * (BL ? 8 : 4 * NR);
         cell0 = warp_base; bars = warp_base + NS * STAGE; cell_bytes = 2u * D;
         active = active_; elect = lane == 0;
@@ -161,7 +162,7 @@ struct SgmPipe {
     __device__ __forceinline__ void fill(const int slot, const uint32_t ic) const {
         if (BULK) {
             if (elect) {
-                bulk_wait_read<NS - PF - 1>();  // the reduce that was issued from this slot NS - PF steps ago has read it
+                if (BULK == 2) bulk_wait_read<NS - PF - 1>();  // the reduce that was issued from this slot NS - PF steps ago has read it
                 mbar_expect_tx(bars + 8 * slot, cell_bytes);
                 bulk_g2s(cell0 + slot * STAGE, C + ic, cell_bytes, bars + 8 * slot);
             }
@@ -178,7 +179,7 @@ struct SgmPipe {
     // L of the cell just computed -> the cell at element index `is` of S; `slot` = the stage its C came from
     __device__ __forceinline__ void emit(const int slot, const uint32_t is, const uint32_t (&L)[NR]) const {
         uint16_t* dst = S + is;
-        if (BULK) {
+        if (BULK == 2) {
             if (active) V::sts(ring + slot * STAGE, L);
             fence_proxy_async_smem();
             __syncwarp();
@@ -191,13 +192,13 @@ struct SgmPipe {
         }
     }
     __device__ __forceinline__ void drain() const {  // shared memory must outlive the bulk reads
-        if (BULK) { if (elect) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); __syncwarp(); }
+        if (BULK == 2) { if (elect) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); __syncwarp(); }
     }
 };
 
 // ---- the accumulate march: specialised at compile time on DIAG (wrap / restart logic only for diagonals), FULL (all 32 lanes
 // active: no predicates) and STORE (plain store vs RED), running 32-bit element cursors instead of recomputed cell indices.
-template <int NR, int PF, bool FULL, bool DIAG, bool STORE, int BL, bool BULK>
+template <int NR, int PF, bool FULL, bool DIAG, bool STORE, int BL, int BULK>
 __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, const int dy, const int line, const int lane, const uint32_t warp_smem,
                                               const int bar_threads, volatile int* s_pace /* [0] rounds finished by this CTA, [1] rounds finished by every CTA */,
                                               const bool leader) {
@@ -282,7 +283,7 @@ __device__ __forceinline__ void sgm_acc_march(const SgmParams& q, const int dx, 
 // bound by the integer pipe): whole ring rounds of NS steps run unrolled, the few steps around an event run one at a time.  The wrap
 // step is a per-line constant, i.e. warp-uniform here.  The CTA barrier / pacing rhythm (every NS steps, same step indices in every
 // warp) is kept, so the warps of a CTA still meet the same number of times.
-template <int NR, int PF, bool FULL, bool STORE, int BL, bool BULK>
+template <int NR, int PF, bool FULL, bool STORE, int BL, int BULK>
 __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const int dx, const int dy, const int line, const int lane,
                                                      const uint32_t warp_smem, const int bar_threads, volatile int* s_pace, const bool leader) {
     using Pipe = SgmPipe<NR, PF, FULL, STORE, BL, BULK>;
@@ -369,7 +370,7 @@ __device__ __forceinline__ void sgm_acc_march_diag32(const SgmParams& q, const i
 // above (below) the block continues from the L its previous owner stored; its minimum is recomputed from that L.  A line whose
 // predecessor cell lies outside the image at the block's first row (the sweep's first row, or a diagonal that has just wrapped) starts
 // fresh exactly as in the whole-frame march.  Column of line x0 after t rows: (x0 + dx * t) mod W.
-template <int NR, int PF, bool FULL, bool STORE, int BL, bool BULK>
+template <int NR, int PF, bool FULL, bool STORE, int BL, int BULK>
 __device__ __forceinline__ void sgm_rows_march(const SgmParams& q, const int dx, const int dy, const int slot_of_dir, const int line, const int lane,
                                                const uint32_t warp_smem, const int bar_threads, volatile int* s_pace, const bool leader) {
     using Pipe = SgmPipe<NR, PF, FULL, STORE, BL, BULK>;
@@ -461,7 +462,7 @@ __device__ __forceinline__ bool sgm_ranged_line(const SgmParams& q, int g, int& 
 }
 
 // 40 registers: 48 resident warps per SM (e.g. two 22-warp CTAs of a paced c4 launch) must fit the 64 K register file
-template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS, bool BULK>
+template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS, int BULK>
 __global__ void __maxnreg__(40)
 k_sgm_acc(SgmParams q) {
     constexpr int RING_BYTES = sgm_warp_smem<NR, PF, BULK>();
@@ -531,7 +532,7 @@ k_sgm_acc(SgmParams q) {
     } else sgm_acc_march<NR, PF, FULL, false, STORE, BL, BULK>(q, dx, dy, line, lane, ring, bar_threads, pace, leader);
 }
 
-template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS, bool BULK>
+template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS, int BULK>
 static int launch_acc_impl(sva_ctx* ctx, const SgmParams& q, const char* name) {
     constexpr size_t RING_BYTES = sgm_warp_smem<NR, PF, BULK>();  // per warp
     constexpr int FALLBACK_WARPS = 8;
@@ -594,12 +595,14 @@ static int launch_acc_impl(sva_ctx* ctx, const SgmParams& q, const char* name) {
     return SVA_OK;
 }
 
-// BULK (the TMA engine's bulk copies) needs a cell to be one contiguous run: every layout except the slice-major volumes of the sliced
-// multi-GPU scheme.  SVA_SGM_BULK=0 selects the per-lane cp.async / RED form (kept for the A/B in profiles/).
+// The bulk forms (the TMA engine's 1-D copies) need a cell to be one contiguous run: every layout except the slice-major volumes of the
+// sliced multi-GPU scheme.  SVA_SGM_BULK = 1 (bulk loads + per-lane REDs) or 2 (bulk loads + bulk reduces); the default, 0, is the per-lane
+// cp.async / RED form, which measured fastest on B200 (profiles/r02_sgm_bulk_ab.txt).
 template <int NR, int PF, bool FULL, bool STORE, int BL, bool ROWS = false>
 static int launch_acc(sva_ctx* ctx, const SgmParams& q, const char* name) {
-    if (ctx->tune_sgm_bulk && q.c_ds == 0) return launch_acc_impl<NR, SGM_PF_BULK, FULL, STORE, BL, ROWS, true>(ctx, q, name);
-    return launch_acc_impl<NR, PF, FULL, STORE, BL, ROWS, false>(ctx, q, name);
+    if (ctx->tune_sgm_bulk == 2 && q.c_ds == 0) return launch_acc_impl<NR, SGM_PF_BULK, FULL, STORE, BL, ROWS, 2>(ctx, q, name);
+    if (ctx->tune_sgm_bulk == 1 && q.c_ds == 0) return launch_acc_impl<NR, PF, FULL, STORE, BL, ROWS, 1>(ctx, q, name);
+    return launch_acc_impl<NR, PF, FULL, STORE, BL, ROWS, 0>(ctx, q, name);
 }
 
 // the directions q.dxs / q.dys in ONE launch; store = plain stores (a single direction that initialises S) instead of REDs
@@ -660,7 +663,7 @@ static void set_dirs(SgmParams& q, const int* idx, int n) {
 static int launch_row_group(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, int n) {
     set_dirs(q, idx, n);
     q.ranged = 0;
-    const size_t ring = (size_t)(SGM_PF + 1) * 32 * 2 * nr * 2 + (ctx->tune_sgm_bulk ? 80 : 0);
+    const size_t ring = (size_t)(SGM_PF + 1) * 32 * 2 * nr * 2 + (ctx->tune_sgm_bulk ? 80 : 0);  // (+ the stages' mbarriers)
     const int cap = ctx->sm_count * std::min(SGM_WARPS_PER_SM, (int)(SGM_SMEM_PER_SM / ring));
     const bool pace = ctx->tune_sgm_pace < 0 ? (size_t)q.W * q.D * 4 >= 768 * 1024 : ctx->tune_sgm_pace != 0;
     if (!pace || n * q.W <= cap || q.W > cap || getenv("SVA_SGM_NO_RANGED")) return launch_dirs(ctx, q, nr, false);

@@ -98,7 +98,8 @@ struct sva_ctx {
                                   // launch share C and S lines in L2 only while their rows stay within the L2-resident window; unpaced drift is harmless
                                   // at c1 (0.66 MB per row: 0.277 ms unpaced, 0.283 paced) and costly at c4 (1.47 MB per row: 1.355 -> 0.925 ms paced).
     int tune_sgm_pace_window = 2; // SVA_SGM_PACE_WINDOW: rounds of 9 rows
-    int tune_sgm_bulk = 1;        // SVA_SGM_BULK: C streams in by the TMA engine's bulk copies + mbarriers and S is accumulated by bulk reduces (0: per-lane cp.async / RED)
+    int tune_sgm_bulk = 0;        // SVA_SGM_BULK: 1 = C streams in by the TMA engine's bulk copies + mbarriers, 2 = and S is accumulated by bulk reduces;
+                                  // 0 (default, fastest measured) = per-lane cp.async / RED
     int tune_sgm_diag_split = 1;  // SVA_SGM_DIAG_SPLIT: diagonal lines run the march that is split at the wrap events (no per-step wrap logic)
     int tune_ad_gather = 0;       // SVA_AD_GATHER=1: force the line-image gather AD kernel (k_ad.cu) even where the image-space kernel applies
     int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)

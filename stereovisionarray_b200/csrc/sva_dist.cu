@@ -34,9 +34,12 @@ struct NcclApi {
 NcclApi* nccl() {
     static NcclApi api;
     if (api.h || !api.err.empty()) return &api;
-    // RTLD_NOLOAD first: a process that already carries an NCCL (torch bundles one) must use THAT copy
+    // RTLD_NOLOAD first: a process that already carries an NCCL (torch bundles one) must use THAT copy.  Otherwise SVA_NCCL_LIB names the
+    // library, else the system's libnccl.so.2 — loaded RTLD_LOCAL so that it does not satisfy another module's NCCL dependency by accident
+    // (a torch imported LATER would bind to it by SONAME all the same: the Python host therefore preloads torch's copy, _lib.py).
     void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_NOLOAD);
-    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+    if (!h && getenv("SVA_NCCL_LIB")) h = dlopen(getenv("SVA_NCCL_LIB"), RTLD_NOW | RTLD_LOCAL);
+    if (!h) h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
     if (!h) { api.err = std::string("dlopen(libnccl.so.2): ") + dlerror(); return &api; }
     bool ok = true;
     auto sym = [&](const char* n) { void* p = dlsym(h, n); if (!p) { ok = false; api.err = std::string("libnccl.so.2 lacks ") + n; } return p; };
