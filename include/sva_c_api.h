@@ -74,8 +74,14 @@ typedef struct sva_params {
     int32_t lr_gx;                  /* 0 = no left-right check; -1/+1 = side of the virtual horizontal other view */
     int32_t lr_max_diff;            /* reject when |d - d_other| > lr_max_diff */
     int32_t subpixel;               /* 0/1: parabolic refinement of the integer winner */
-    int32_t reserved[8];
+    int32_t reserved[8];            /* reserved[0] = matching cost (sva_cost_mode, default SVA_COST_SAD); the rest must be 0 */
 } sva_params;
+
+/* Per-pixel matching cost that K1a sums over the pairs (the box window, shift / cap, SGM and WTA are the same for both).
+ * SVA_COST_SAD: |R - I_k| — getAbsDiff, src/functions.cpp:215-218.  SVA_COST_CENSUS: Hamming distance of 9 x 7 census signatures (62 bits;
+ * bit = neighbour < centre, out-of-image = 0) — named by north_star, absent from the reference: spec frozen in oracle/sva_oracle.c, parity
+ * unpinned by the reference. */
+typedef enum sva_cost_mode { SVA_COST_SAD = 0, SVA_COST_CENSUS = 1 } sva_cost_mode;
 
 typedef struct sva_ctx sva_ctx;
 

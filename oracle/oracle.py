@@ -138,6 +138,12 @@ class Oracle:
     def _shape(self, p):
         return (p.height, p.width, p.num_disp)
 
+    def census_transform(self, img):
+        i, ik = abi.image_u8(np.ascontiguousarray(img, dtype=np.uint8))
+        out = np.zeros(ik.shape, dtype=np.uint64)
+        self.lib.orc_census_transform(C.byref(i), _ptr(out, C.c_uint64))
+        return out
+
     def ad_volume(self, p, ref, others, pair_begin=0, pair_end=None):
         r, rk = abi.image_u8(np.ascontiguousarray(ref, dtype=np.uint8))
         o, ok = abi.image_array(others)

@@ -303,10 +303,74 @@ int orc_cell_valid(const sva_params* p, int y, int x, int d) {
     return 1;
 }
 
+/* ---- census cost mode (p->reserved[0] == SVA_COST_CENSUS) -----------------------------------------------------------------------------
+ * north_star names a "census/SAD matching cost"; the reference has only SAD (src/functions.cpp:215-218), so this mode is PARITY UNPINNED BY
+ * THE REFERENCE: the spec below is this repository's own (Zabih & Woodfill 1994 as used with SGM by Hirschmueller 2008), frozen here.
+ *   signature T(y,x): 62 bits, one per neighbour (dy in [-3,3], dx in [-4,4], centre excluded, row-major, bit 0 first):
+ *                     bit = 1 iff I(y+dy, x+dx) < I(y,x); a neighbour outside the image reads as 0.
+ *   per-pixel cost  : A(y,x,d) = sum_k popcount(T_R(y,x) XOR T_k(y - gy_k*delta, x - gx_k*delta)); a source pixel outside the image has
+ *                     signature 0.  <= 62 * 32 fits u16.
+ * Everything after A (box sum over the 2k x 2k window, shift / cap, validity, SGM, WTA) is the same as for SAD. */
+#define ORC_CENSUS_RX 4
+#define ORC_CENSUS_RY 3
+void orc_census_transform(const sva_image_u8* img, uint64_t* out) {
+    const int W = img->cols, H = img->rows;
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const int c = img->data[(size_t)y * img->step + x];
+            uint64_t t = 0;
+            int bit = 0;
+            for (int dy = -ORC_CENSUS_RY; dy <= ORC_CENSUS_RY; dy++)
+                for (int dx = -ORC_CENSUS_RX; dx <= ORC_CENSUS_RX; dx++) {
+                    if (dx == 0 && dy == 0) continue;
+                    const int yy = y + dy, xx = x + dx;
+                    const int v = (yy >= 0 && yy < H && xx >= 0 && xx < W) ? img->data[(size_t)yy * img->step + xx] : 0;
+                    if (v < c) t |= (uint64_t)1 << bit;
+                    bit++;
+                }
+            out[(size_t)y * W + x] = t;
+        }
+}
+
+static int census_ad_volume(const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, int32_t pair_begin, int32_t pair_end, uint16_t* A) {
+    const int W = p->width, H = p->height, D = p->num_disp;
+    const size_t px = (size_t)W * H;
+    uint64_t* tr = (uint64_t*)malloc(px * sizeof(uint64_t));
+    uint64_t* to = (uint64_t*)malloc(px * sizeof(uint64_t) * (size_t)(pair_end - pair_begin > 0 ? pair_end - pair_begin : 1));
+    if (!tr || !to) { free(tr); free(to); return SVA_ERR_NOMEM; }
+    orc_census_transform(ref, tr);
+    for (int i = pair_begin; i < pair_end; i++) orc_census_transform(&others[i], to + px * (size_t)(i - pair_begin));
+#ifdef _OPENMP
+#pragma omp parallel for schedule(static)
+#endif
+    for (int y = 0; y < H; y++)
+        for (int x = 0; x < W; x++) {
+            const uint64_t r = tr[(size_t)y * W + x];
+            uint16_t* a = A + ((size_t)y * W + x) * D;
+            for (int d = 0; d < D; d++) {
+                int delta = p->min_disp + d, s = 0;
+                for (int i = pair_begin; i < pair_end; i++) {
+                    int sx = x - p->pair_gx[i] * delta, sy = y - p->pair_gy[i] * delta;
+                    uint64_t v = 0;
+                    if (sx >= 0 && sx < W && sy >= 0 && sy < H) v = to[px * (size_t)(i - pair_begin) + (size_t)sy * W + sx];
+                    s += __builtin_popcountll(r ^ v);
+                }
+                a[d] = (uint16_t)s;
+            }
+        }
+    free(tr); free(to);
+    return SVA_OK;
+}
+
 /* A(y,x,d) = sum over pairs [pair_begin, pair_end) of |R(y,x) - I_k(y - gy*delta, x - gx*delta)|; a source pixel outside
- * the image reads as 0.  Exact u16 (<= 255 * 32). */
+ * the image reads as 0.  Exact u16 (<= 255 * 32).  (Census mode: the Hamming form above.) */
 int orc_ad_volume(const sva_params* p, const sva_image_u8* ref, const sva_image_u8* others, int32_t pair_begin, int32_t pair_end, uint16_t* A) {
     if (!params_ok(p) || pair_begin < 0 || pair_end > p->n_pairs) return SVA_ERR_BAD_ARG;
+    if (p->reserved[0] == SVA_COST_CENSUS) return census_ad_volume(p, ref, others, pair_begin, pair_end, A);
+    if (p->reserved[0] != SVA_COST_SAD) return SVA_ERR_BAD_ARG;
     const int W = p->width, H = p->height, D = p->num_disp;
 #ifdef _OPENMP
 #pragma omp parallel for schedule(static)

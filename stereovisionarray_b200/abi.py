@@ -24,6 +24,7 @@ SVA_IPC_HANDLE_BYTES = 64
 ORTHOGONAL, DIAGONAL, TO_CENTER, LINE_HORIZONTAL, LINE_VERTICAL, CROSS, JUMP_CROSS, TO_CENTER_SMALL, MID_LEFT, MID_TOP = range(10)
 
 STAGE_AD, STAGE_BOX, STAGE_SGM, STAGE_ALL = 1, 2, 3, 100
+COST_SAD, COST_CENSUS = 0, 1  # sva_cost_mode (params.reserved[0])
 
 
 class SvaCamera(C.Structure):
@@ -47,16 +48,16 @@ class SvaParams(C.Structure):
 
 
 def make_params(width, height, num_disp, pairs, win_half=20, min_disp=0, cost_shift=None, cost_cap=SVA_COST_CAP_MAX,
-                p1=None, p2=None, n_paths=8, lr_gx=0, lr_max_diff=1, subpixel=1):
+                p1=None, p2=None, n_paths=8, lr_gx=0, lr_max_diff=1, subpixel=1, cost_mode=COST_SAD):
     """pairs: list of (gx, gy) grid offsets of the other cameras.  Defaults follow SURVEY §8(d):
-    P1 = 8*Np, P2 = 32*Np in PACK_U16 units; shift = smallest s with (4k^2 * 255 * Np) >> s <= cap."""
+    P1 = 8*Np, P2 = 32*Np in PACK_U16 units; shift = smallest s with (4k^2 * 255 * Np) >> s <= cap (census: 62 instead of 255)."""
     p = SvaParams()
     p.width, p.height, p.num_disp, p.min_disp, p.win_half = width, height, num_disp, min_disp, win_half
     p.n_pairs = len(pairs)
     for i, (gx, gy) in enumerate(pairs):
         p.pair_gx[i], p.pair_gy[i] = gx, gy
     if cost_shift is None:
-        full = 4 * win_half * win_half * 255 * len(pairs)
+        full = 4 * win_half * win_half * (62 if cost_mode == COST_CENSUS else 255) * len(pairs)
         cost_shift = 0
         while (full >> cost_shift) > cost_cap:
             cost_shift += 1
@@ -64,6 +65,7 @@ def make_params(width, height, num_disp, pairs, win_half=20, min_disp=0, cost_sh
     p.p1 = 8 * len(pairs) if p1 is None else p1
     p.p2 = 32 * len(pairs) if p2 is None else p2
     p.n_paths, p.lr_gx, p.lr_max_diff, p.subpixel = n_paths, lr_gx, lr_max_diff, subpixel
+    p.reserved[0] = cost_mode
     return p
 
 

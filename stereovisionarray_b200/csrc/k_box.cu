@@ -10,8 +10,6 @@
 // subtract the row leaving it).  The horizontal window sum is a difference of row prefix sums: every thread scans its
 // own NC columns in registers, segment totals are exchanged through shared memory, and the prefix row P lives in
 // shared memory for the two look-ups P[x+k-1] - P[x-k-1].  All sums are exact u32.
-#include <cstdlib>
-
 #include "sva_common.cuh"
 
 #define BOX_THREADS 256
@@ -222,26 +220,8 @@ struct BoxPParams {
     int ry0, ry1;  // output rows [ry0, ry1) (the whole image, or a row block)
 };
 
-// L2 eviction hints (HINT): the row ENTERING the window is read again 2k rows later as the LEAVING row — keep it (evict_last); after that second
-// read it is dead (evict_first), and the rows of C written here are not read before the next kernel has streamed far more than the L2 holds
-// (evict_first), so they must not push the window's rows out.
-__device__ __forceinline__ uint4 ldg_hint_u128(const void* p, const uint64_t pol) {
-    uint4 v;
-    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v4.u32 {%0, %1, %2, %3}, [%4], %5;" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p), "l"(pol));
-    return v;
-}
-__device__ __forceinline__ void stg_hint_u128(void* p, const uint4 v, const uint64_t pol) {
-    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(pol) : "memory");
-}
-
-template <int MINB, int HINT>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(256, 2)
 k_box_planar(BoxPParams q) {
-    uint64_t pol_keep = 0, pol_drop = 0;
-    if (HINT) {
-        asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol_keep));
-        asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol_drop));
-    }
     __shared__ __align__(16) uint32_t s_out[2][BXP_WARPS][BXP_OPITCH];
     __shared__ uint2 s_T[BXP_WARPS][8 * BXP_TCOLS];
     __shared__ int s_limy[BXP_MAX_BAND];
@@ -348,29 +328,20 @@ k_box_planar(BoxPParams q) {
         *reinterpret_cast<uint4*>(so + 4) = make_uint4(w[4], w[5], w[6], w[7]);
         __syncthreads();  // one barrier per row: s_out is double-buffered
         const uint32_t* src = &s_out[it & 1][4 * hf][xl0];
-        const uint4 o0 = make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]);
-        const uint4 o1 = make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]);
-        if (HINT) {
-            if (st0) stg_hint_u128(po, o0, pol_drop);
-            if (st1) stg_hint_u128(po + 128 * D, o1, pol_drop);
-        } else {
-            if (st0) *reinterpret_cast<uint4*>(po) = o0;
-            if (st1) *reinterpret_cast<uint4*>(po + 128 * D) = o1;
-        }
+        if (st0) *reinterpret_cast<uint4*>(po) = make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]);
+        if (st1) *reinterpret_cast<uint4*>(po + 128 * D) = make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]);
         po += orow;
     };
 
     // software pipeline, unrolled by two so the row buffers ping-pong without register moves
-    auto ld_enter = [&](const uint32_t* p) { return HINT ? ldg_hint_u128(p, pol_keep) : ldg_stream_u128(p); };
-    auto ld_leave = [&](const uint32_t* p) { return HINT ? ldg_hint_u128(p, pol_drop) : ldg_stream_u128(p); };
-    uint4 a0 = ld_enter(pe), a1 = ld_enter(pe + 4), al0 = make_uint4(0, 0, 0, 0), al1 = al0;
+    uint4 a0 = ldg_stream_u128(pe), a1 = ldg_stream_u128(pe + 4), al0 = make_uint4(0, 0, 0, 0), al1 = al0;
     uint4 b0 = a0, b1 = a1, bl0 = al0, bl1 = al1;
     auto fetch = [&](const int n, uint4& e0, uint4& e1, uint4& l0, uint4& l1) {  // loads of update n
         if (n < N) {
             pe += q.row_words;
             const uint32_t* pl = n >= 2 * k ? pe - back : pz;
-            e0 = ld_enter(pe); e1 = ld_enter(pe + 4);
-            l0 = ld_leave(pl); l1 = ld_leave(pl + 4);
+            e0 = ldg_stream_u128(pe); e1 = ldg_stream_u128(pe + 4);
+            l0 = ldg_stream_u128(pl); l1 = ldg_stream_u128(pl + 4);
         }
     };
     for (int n = 0; n < N; n += 2) {
@@ -402,10 +373,8 @@ static int sva_launch_box_planar(sva_ctx* ctx) {
     const int strips = ctx->ap.strips, dgroups = div_up(D, 16);
     // Row bands: every band re-reads 2k-1 warm-up rows, and the grid should fill whole waves of the resident CTAs.  Pick the band
     // count that minimises waves x rows marched per CTA.
-    static const int minb = getenv("SVA_BOX_MINB") ? atoi(getenv("SVA_BOX_MINB")) : 2, hint = getenv("SVA_BOX_HINT") ? atoi(getenv("SVA_BOX_HINT")) : 0;
-    void (*kern)(BoxPParams) = minb == 3 ? (hint ? k_box_planar<3, 1> : k_box_planar<3, 0>) : (hint ? k_box_planar<2, 1> : k_box_planar<2, 0>);
     int per_sm = 2;
-    SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, 256, 0));
+    SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_box_planar, 256, 0));
     if (per_sm < 1) per_sm = 1;
     const int slots = per_sm * ctx->sm_count, per_band = strips * dgroups;
     int bands = 1;
@@ -422,7 +391,7 @@ static int sva_launch_box_planar(sva_ctx* ctx) {
         if (cost < best) { best = cost; bands = nb; q.band_rows = rows; }
     }
     LaunchScope ls(ctx, "k_box_planar");
-    kern<<<dim3(strips, dgroups, bands), 256, 0, ctx->stream>>>(q);
+    k_box_planar<<<dim3(strips, dgroups, bands), 256, 0, ctx->stream>>>(q);
     SVA_CUDA_OK(ctx, cudaGetLastError());
     return SVA_OK;
 }

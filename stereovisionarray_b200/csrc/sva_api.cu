@@ -14,6 +14,7 @@ struct NvtxRange {
 
 int sva_build_line_images(sva_ctx* ctx);
 int sva_run_ad(sva_ctx* ctx);
+int sva_run_ad_census(sva_ctx* ctx);
 int sva_run_box(sva_ctx* ctx, bool raw);
 int sva_run_sgm(sva_ctx* ctx);
 int sva_sgm_regs_per_lane(int D);
@@ -39,7 +40,9 @@ static int check_params(sva_ctx* c, const sva_params* p) {
     if (p->n_paths != 0 && p->n_paths != 4 && p->n_paths != 8) return c->fail(SVA_ERR_BAD_ARG, "n_paths must be 0, 4 or 8");
     if (p->lr_gx < -1 || p->lr_gx > 1) return c->fail(SVA_ERR_BAD_ARG, "lr_gx must be -1, 0 or +1");
     if (sva_sgm_regs_per_lane(p->num_disp) == 0) return c->fail(SVA_ERR_BAD_ARG, "unsupported num_disp");
-    // exact u32 box sums: 4k^2 * 255 * n_pairs must fit
+    if (p->reserved[0] != SVA_COST_SAD && p->reserved[0] != SVA_COST_CENSUS) return c->fail(SVA_ERR_BAD_ARG, "unknown cost mode (reserved[0])");
+    for (int i = 1; i < 8; i++) if (p->reserved[i] != 0) return c->fail(SVA_ERR_BAD_ARG, "reserved parameter fields must be zero");
+    // exact u32 box sums: 4k^2 * 255 * n_pairs must fit (census cells are smaller still)
     if (4.0 * p->win_half * p->win_half * 255.0 * p->n_pairs > 4.0e9) return c->fail(SVA_ERR_BAD_ARG, "window sum overflows u32");
     // the marches index the volumes with 32-bit element cursors
     if ((double)p->width * p->height * p->num_disp >= 4294967296.0) return c->fail(SVA_ERR_BAD_ARG, "frame too large: width * height * num_disp must be below 2^32");
@@ -85,7 +88,8 @@ int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, c
     c->s_prezeroed = false;
     c->ad_y0 = c->ad_y1 = c->cost_y0 = c->cost_y1 = 0;
     const size_t img = (size_t)W * H;
-    c->use_ad2 = sva_ad2_usable(*p) && !c->tune_ad_gather;
+    const bool census = p->reserved[0] == SVA_COST_CENSUS;
+    c->use_ad2 = sva_ad2_usable(*p) && !c->tune_ad_gather && !census;
     if (c->use_ad2) {
         // image-space AD kernel: the views go straight from the host into zero-bordered, 16-byte-pitched device copies
         SVA_TRY(sva_ad2_prepare(c));
@@ -104,7 +108,7 @@ int sva_frame_upload(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, c
         SVA_TRY(c->reserve(c->mask, img));
         SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->mask.p, W, mask->data, mask->step, W, H, cudaMemcpyHostToDevice, c->stream));
     }
-    if (!c->use_ad2) SVA_TRY(sva_build_line_images(c));
+    if (!c->use_ad2 && !census) SVA_TRY(sva_build_line_images(c));
     c->have_frame = true;
     return SVA_OK;
 }
@@ -151,7 +155,7 @@ static int run_stage(sva_ctx* c, int stage) {
             if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
             if (!c->ad_params_ok)
                 return c->fail(SVA_ERR_STATE, "sva_frame_set_params changed the pairs / disparity reach the views were staged for at upload: upload the frame again before SVA_STAGE_AD");
-            SVA_TRY(c->use_ad2 ? sva_run_ad2(c) : sva_run_ad(c));
+            SVA_TRY(c->prm.reserved[0] == SVA_COST_CENSUS ? sva_run_ad_census(c) : c->use_ad2 ? sva_run_ad2(c) : sva_run_ad(c));
             // rows of A that now hold this frame: the block's rows +- win_half (clipped), or everything
             const int H = c->prm.height, k = c->prm.win_half;
             if (c->pair_begin != 0 || c->pair_end != c->prm.n_pairs) c->ad_y0 = c->ad_y1 = 0;  // a pair-range partial replaces what A held
@@ -359,7 +363,7 @@ int sva_frame_set_params(sva_ctx* c, const sva_params* p) {
     // Other parameter sets (e.g. the full range after a disparity-slice cost volume, for SGM / WTA) are accepted, but SVA_STAGE_AD then
     // needs a new upload.
     const sva_params& u = c->up_prm;
-    bool same = p->n_pairs == u.n_pairs && p->min_disp == u.min_disp && p->win_half == u.win_half && (p->num_disp + 31) / 32 <= (u.num_disp + 31) / 32;
+    bool same = p->reserved[0] == u.reserved[0] && p->n_pairs == u.n_pairs && p->min_disp == u.min_disp && p->win_half == u.win_half && (p->num_disp + 31) / 32 <= (u.num_disp + 31) / 32;
     for (int i = 0; same && i < p->n_pairs; i++) same = p->pair_gx[i] == u.pair_gx[i] && p->pair_gy[i] == u.pair_gy[i];
     c->ad_params_ok = same;
     c->ad_y0 = c->ad_y1 = c->cost_y0 = c->cost_y1 = 0;
@@ -462,7 +466,7 @@ int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, 
     const int64_t t = c->stream_ticket;
     const int slot = (int)(t & 1);
     if (t > 0 && p && (p->width != c->prm.width || p->height != c->prm.height || p->num_disp != c->prm.num_disp || p->n_pairs != c->prm.n_pairs ||
-                       p->win_half != c->prm.win_half || p->min_disp != c->prm.min_disp)) {
+                       p->win_half != c->prm.win_half || p->min_disp != c->prm.min_disp || p->reserved[0] != c->prm.reserved[0])) {
         // a different geometry re-allocates workspaces: drain the pipeline first so no frame in flight still uses the old ones
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->h2d_stream));
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -106,7 +106,7 @@ struct sva_ctx {
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
-    DevBuf pad_imgs, pad_ref, comm_scratch;
+    DevBuf pad_imgs, pad_ref, comm_scratch, census;
     // ---- multi-GPU (sva_dist.cu) ----
     void* comm = nullptr;        // ncclComm_t (sva_comm_init)
     int comm_rank = 0, comm_world = 1;

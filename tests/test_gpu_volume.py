@@ -294,3 +294,37 @@ def test_state_guards_of_the_staged_api(ctx, oracle):
     d, s = ctx.download_disparity()
     d_o, s_o = oracle.depth_from_array(p, sc["ref"], sc["others"])
     assert np.array_equal(d, d_o) and np.array_equal(s, s_o)
+
+
+@pytest.mark.parametrize("h,w,D,offs,kw", [(64, 96, 64, OFF8, dict(win_half=4, n_paths=8, lr_gx=-1)), (57, 203, 40, [(-1, 0), (2, 1), (0, -3)], dict(win_half=2, n_paths=4, lr_gx=1, min_disp=3)),
+                                           (70, 150, 192, OFF15, dict(win_half=5, n_paths=8, lr_gx=-1))])
+def test_census_cost_mode_bit_exact(ctx, oracle, h, w, D, offs, kw):
+    """census cost (north_star names it; no reference counterpart: parity is against the spec frozen in the oracle): Hamming volume, cost
+    volume and the maps of the whole pipeline, plus pair-range partials (the pair-sharded reduce) and the one-call path"""
+    sc = synth.make_scene(h, w, D, offs, 640 + D, min_disp=kw.get("min_disp", 0), face=True)
+    p = abi.make_params(w, h, D, offs, cost_mode=abi.COST_CENSUS, **kw)
+    ctx.set_debug(1, 0)
+    ctx.upload(p, sc["ref"], sc["others"], sc["mask"])
+    ctx.run(abi.STAGE_AD)
+    A_o = oracle.ad_volume(p, sc["ref"], sc["others"])
+    assert np.array_equal(ctx.download_ad(), A_o), "Hamming volume"
+    ctx.run(abi.STAGE_BOX)
+    C_o = oracle.box_cost(p, A_o)
+    assert np.array_equal(ctx.download_cost(), C_o), "cost volume"
+    ctx.run(abi.STAGE_SGM)
+    S_o = oracle.sgm_aggregate(p, C_o)
+    assert np.array_equal(ctx.download_sgm(), S_o)
+    disp, sub = ctx.download_disparity()
+    disp_o, sub_o = oracle.wta(p, S_o, sc["mask"])
+    assert np.array_equal(disp, disp_o) and np.array_equal(sub, sub_o)
+    ctx.set_debug(0, 0)
+    if len(offs) > 2:
+        ctx.set_pair_range(1, len(offs))
+        ctx.run(abi.STAGE_AD)
+        assert np.array_equal(ctx.download_ad(), oracle.ad_volume(p, sc["ref"], sc["others"], 1, len(offs)))
+    d1, s1 = ctx.depth_from_array(p, sc["ref"], sc["others"], sc["mask"])
+    assert np.array_equal(d1, disp_o) and np.array_equal(s1, sub_o)
+    # and back to SAD on the same context
+    p_sad = abi.make_params(w, h, D, offs, **kw)
+    d2, _ = ctx.depth_from_array(p_sad, sc["ref"], sc["others"], sc["mask"])
+    assert np.array_equal(d2, oracle.depth_from_array(p_sad, sc["ref"], sc["others"], sc["mask"])[0])

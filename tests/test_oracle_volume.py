@@ -207,3 +207,66 @@ def test_sgm_rows_blocks_equal_the_whole_path(oracle):
     # a block that continues a sweep refuses to run without the state
     with pytest.raises(AssertionError):
         oracle.sgm_rows(p, Cv, 0, 5, 4, None, np.zeros_like(whole), None)
+
+
+def _census_numpy(img):
+    """independent restatement of the census signature: 9 x 7 window, bit = neighbour < centre, outside = 0, row-major without the centre"""
+    h, w = img.shape
+    pad = np.zeros((h + 6, w + 8), np.int32)
+    pad[3:3 + h, 4:4 + w] = img
+    c = img.astype(np.int32)
+    t = np.zeros((h, w), np.uint64)
+    bit = 0
+    for dy in range(-3, 4):
+        for dx in range(-4, 5):
+            if dx == 0 and dy == 0:
+                continue
+            nb = pad[3 + dy:3 + dy + h, 4 + dx:4 + dx + w]
+            t |= (nb < c).astype(np.uint64) << np.uint64(bit)
+            bit += 1
+    assert bit == 62
+    return t
+
+
+def test_census_cost_mode(oracle):
+    """census mode (north_star names it, the reference has none: parity unpinned by the reference): signatures and the Hamming volume against
+    independent numpy restatements; the rest of the pipeline is shared with SAD.  Unlike SAD, the cost ignores a gain / offset between cameras:
+    with the other views darkened, census still recovers the ground truth where SAD does not."""
+    h, w, D = 48, 72, 24
+    offs = [(-1, 0), (1, 0), (0, -1), (1, 1)]
+    sc = synth.make_scene(h, w, D, offs, 21)
+    p = abi.make_params(w, h, D, offs, win_half=3, n_paths=8, lr_gx=-1, cost_mode=abi.COST_CENSUS)
+    assert p.reserved[0] == abi.COST_CENSUS and p.cost_shift == 2  # 36 * 62 * 4 = 8928: two shifts bring the largest window sum under the cap of 4095
+    tr = oracle.census_transform(sc["ref"])
+    assert np.array_equal(tr, _census_numpy(sc["ref"]))
+    assert int(tr.max()) < (1 << 62)
+    A = oracle.ad_volume(p, sc["ref"], sc["others"])
+    to = [_census_numpy(o) for o in sc["others"]]
+    exp = np.zeros((h, w, D), np.int64)
+    ys, xs = np.mgrid[0:h, 0:w]
+    for d in range(D):
+        for (gx, gy), t in zip(offs, to):
+            sh = np.zeros((h, w), np.uint64)
+            sy, sx = ys - gy * d, xs - gx * d
+            ok = (sy >= 0) & (sy < h) & (sx >= 0) & (sx < w)
+            sh[ok] = t[sy[ok], sx[ok]]
+            x = tr ^ sh
+            exp[:, :, d] += np.array([bin(int(v)).count("1") for v in x.ravel()]).reshape(h, w)
+    assert np.array_equal(A.astype(np.int64), exp)
+    assert int(A.max()) <= 62 * len(offs)
+    # pair-range partials add up (what pair sharding relies on), as for SAD
+    assert np.array_equal(oracle.ad_volume(p, sc["ref"], sc["others"], 0, 1) + oracle.ad_volume(p, sc["ref"], sc["others"], 1, 4), A)
+    # robustness to a radiometric difference between the cameras: darkened other views cost SAD half of its correct pixels, census none
+    h, w, D = 96, 144, 32
+    sc = synth.make_scene(h, w, D, offs, 22)
+    dark = [np.clip(o.astype(np.int32) * 6 // 10 + 9, 0, 255).astype(np.uint8) for o in sc["others"]]
+    res = {}
+    for name, views in (("clean", sc["others"]), ("dark", dark)):
+        for mode in (abi.COST_SAD, abi.COST_CENSUS):
+            pm = abi.make_params(w, h, D, offs, win_half=3, n_paths=8, lr_gx=0, cost_mode=mode)
+            disp, _ = oracle.depth_from_array(pm, sc["ref"], views)
+            valid = disp != abi.SVA_DISP_INVALID
+            res[name, mode] = float((np.abs(disp[valid].astype(np.int32) - sc["gt"][valid]) <= 1).mean())
+    assert abs(res["dark", abi.COST_CENSUS] - res["clean", abi.COST_CENSUS]) < 0.02, res
+    assert res["dark", abi.COST_SAD] < res["clean", abi.COST_SAD] - 0.2, res
+    assert res["clean", abi.COST_CENSUS] > res["clean", abi.COST_SAD] - 0.05, res
