@@ -15,10 +15,12 @@ __global__ void k_abs_diff(const uint8_t* __restrict__ a, size_t apitch, const u
 }
 
 // ---- K0: shiftPerspectiveWithDisparity — reference src/functions.cpp:55-77 -------------------------------------------
-// out(y,x) = img(int(d*uy + y), int(d*ux + x)), skipping d == 0 and out-of-bounds sources (zero there).  The f64 multiply-add
-// is written with explicit round-to-nearest intrinsics so no FMA contraction can change the truncation.
-__global__ void k_shift_perspective(const uint8_t* __restrict__ disp, const uint8_t* __restrict__ img, int W, int H, double ux, double uy,
-                                    uint8_t* __restrict__ out) {
+// out(y,x) = img(int(d*uy + y), int(d*ux + x)), skipping d == 0 and out-of-bounds sources (zero there).  A TEXTURE GATHER: the source view
+// is bound as a 2-D texture object (point sampling, unnormalised coordinates, border addressing), so the data-dependent reads go through
+// the texture path and a source outside the image returns the border value 0 — the reference's bounds test `:66-69` in hardware.  The
+// source coordinate itself is the reference's f64 expression, with explicit round-to-nearest intrinsics so that no FMA contraction can
+// change the truncation; integer coordinates + 0.5 are exact in f32 for any image the texture unit can hold.
+__global__ void k_shift_perspective(const uint8_t* __restrict__ disp, cudaTextureObject_t img, int W, int H, double ux, double uy, uint8_t* __restrict__ out) {
     int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y;
     if (x >= W) return;
     uint8_t d8 = disp[(size_t)y * W + x];
@@ -27,7 +29,7 @@ __global__ void k_shift_perspective(const uint8_t* __restrict__ disp, const uint
         double d = (double)d8;
         int sx = (int)__dadd_rn(__dmul_rn(d, ux), (double)x);
         int sy = (int)__dadd_rn(__dmul_rn(d, uy), (double)y);
-        if (sy < H && sy >= 0 && sx < W && sx >= 0) v = __ldg(img + (size_t)sy * W + sx);
+        v = tex2D<unsigned char>(img, (float)sx + 0.5f, (float)sy + 0.5f);
     }
     out[(size_t)y * W + x] = v;
 }
@@ -100,8 +102,36 @@ int sva_abs_diff_u8(sva_ctx* c, const sva_image_u8* a, const sva_image_u8* b, do
     return SVA_OK;
 }
 
-// device-side core shared by the public call and improveWithDisparity: d_disp, d_img, d_out are W*H u8 in HBM
-static int shift_perspective_dev(sva_ctx* c, const sva_camera* in_cam, const sva_camera* out_cam, const uint8_t* d_disp, const uint8_t* d_img, int W, int H,
+// The view to be warped, as a texture: uploaded into a pitched buffer of the context (the pitch a 2-D texture needs) and bound once per
+// buffer / geometry; later uploads of the same geometry reuse the object (stream order keeps kernel and copy apart).
+static int texture_upload(sva_ctx* c, const sva_image_u8* im, cudaTextureObject_t* out) {
+    const int W = im->cols, H = im->rows;
+    const size_t pitch = ((size_t)W + 511) & ~(size_t)511;
+    SVA_TRY(c->reserve(c->tex_img, pitch * H));
+    const uint64_t key = ((uint64_t)(uintptr_t)c->tex_img.p * 1000003u + (uint64_t)W) * 1000003u + (uint64_t)H;
+    if (key != c->tex_key || !c->tex) {
+        if (c->tex) { SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream)); cudaDestroyTextureObject(c->tex); c->tex = 0; }
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypePitch2D;
+        rd.res.pitch2D.devPtr = c->tex_img.p;
+        rd.res.pitch2D.desc = cudaCreateChannelDesc<unsigned char>();
+        rd.res.pitch2D.width = W; rd.res.pitch2D.height = H; rd.res.pitch2D.pitchInBytes = pitch;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeBorder;  // outside the image: 0
+        td.filterMode = cudaFilterModePoint;
+        td.readMode = cudaReadModeElementType;
+        td.normalizedCoords = 0;
+        cudaTextureObject_t t = 0;
+        SVA_CUDA_OK(c, cudaCreateTextureObject(&t, &rd, &td, nullptr));
+        c->tex = (unsigned long long)t; c->tex_key = key;
+    }
+    SVA_CUDA_OK(c, cudaMemcpy2DAsync(c->tex_img.p, pitch, im->data, im->step, W, H, cudaMemcpyHostToDevice, c->stream));
+    *out = (cudaTextureObject_t)c->tex;
+    return SVA_OK;
+}
+
+// device-side core shared by the public call and improveWithDisparity: d_disp, d_out are W*H u8 in HBM, d_img the view as a texture
+static int shift_perspective_dev(sva_ctx* c, const sva_camera* in_cam, const sva_camera* out_cam, const uint8_t* d_disp, cudaTextureObject_t d_img, int W, int H,
                                  uint8_t* d_out) {
     double dx = in_cam->pos[0] - out_cam->pos[0], dy = in_cam->pos[1] - out_cam->pos[1], dz = in_cam->pos[2] - out_cam->pos[2];
     double dist = sqrt(dx * dx + dy * dy + dz * dz);  // host TU is built with -ffp-contract=off (:58,61-62)
@@ -122,9 +152,10 @@ int sva_shift_perspective_with_disparity(sva_ctx* c, const sva_camera* input_cam
     size_t n = (size_t)W * H;
     SVA_TRY(c->reserve(c->scratch, 3 * n));
     SVA_TRY(upload_u8(c, c->scratch, 0, disparity));
-    SVA_TRY(upload_u8(c, c->scratch, n, image));
+    cudaTextureObject_t tex = 0;
+    SVA_TRY(texture_upload(c, image, &tex));
     uint8_t* base = c->scratch.as<uint8_t>();
-    SVA_TRY(shift_perspective_dev(c, input_cam, output_cam, base, base + n, W, H, base + 2 * n));
+    SVA_TRY(shift_perspective_dev(c, input_cam, output_cam, base, tex, W, H, base + 2 * n));
     SVA_CUDA_OK(c, cudaMemcpyAsync(out, base + 2 * n, n, cudaMemcpyDeviceToHost, c->stream));
     SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
     return SVA_OK;
@@ -151,7 +182,7 @@ int sva_improve_with_disparity(sva_ctx* c, const sva_image_u8* disparity, const 
     const size_t npx = (size_t)W * H;
     SVA_TRY(c->reserve(c->scratch, 6 * npx));
     uint8_t* base = c->scratch.as<uint8_t>();
-    uint8_t *d_disp = base, *d_center = base + npx, *d_mask = base + 2 * npx, *d_img = base + 3 * npx, *d_shift = base + 4 * npx, *d_out = base + 5 * npx;
+    uint8_t *d_disp = base, *d_center = base + npx, *d_mask = base + 2 * npx, *d_shift = base + 4 * npx, *d_out = base + 5 * npx;
     SVA_TRY(upload_u8(c, c->scratch, 0, disparity));
     SVA_TRY(upload_u8(c, c->scratch, npx, center));
     SVA_TRY(upload_u8(c, c->scratch, 2 * npx, mask));
@@ -167,8 +198,9 @@ int sva_improve_with_disparity(sva_ctx* c, const sva_image_u8* disparity, const 
             if (x0 - k - 5 * dirx < 0 || y0 - k - 5 * diry < 0 || x1 + k + 5 * dirx > W || y1 + k + 5 * diry > H)
                 return c->fail(SVA_ERR_ROI, "improveWithDisparity: a masked pixel's window leaves the image (the reference throws cv::Exception here)");
         }
-        SVA_TRY(upload_u8(c, c->scratch, 3 * npx, &images[i]));
-        SVA_TRY(shift_perspective_dev(c, c0, c1, d_disp, d_img, W, H, d_shift));
+        cudaTextureObject_t tex = 0;
+        SVA_TRY(texture_upload(c, &images[i], &tex));
+        SVA_TRY(shift_perspective_dev(c, c0, c1, d_disp, tex, W, H, d_shift));
         {
             LaunchScope ls(c, "k_refine_planes");
             k_refine_planes<<<dim3(div_up(W, 128), H), 128, 0, c->stream>>>(d_center, d_shift, W, H, dirx, diry, c->A.as<uint16_t>());

@@ -26,7 +26,7 @@ void sva_ctx::release(DevBuf& b) {
 }
 
 void sva_ctx::device_bufs(std::vector<DevBuf*>& out) {
-    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf, &comm_scratch, &census,
+    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf, &comm_scratch, &census, &tex_img,
            &alt.pad_ref, &alt.pad_imgs, &alt.ref_img, &alt.other_imgs, &alt.lines, &alt.mask, &alt.disp, &alt.subpix};
 }
 
@@ -112,6 +112,7 @@ int sva_destroy(sva_ctx* c) {
     cudaSetDevice(c->device);
     cudaStreamSynchronize(c->stream);
     sva_dist_release(c);
+    if (c->tex) cudaDestroyTextureObject((cudaTextureObject_t)c->tex);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(c->d2h_stream); }
     std::vector<DevBuf*> bufs;
