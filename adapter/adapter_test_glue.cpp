@@ -7,7 +7,14 @@
 #include "functions.h"
 #include "dlibFaceSelect.h"
 
+#include "sva_c_api.h"
+
 cv::Mat svaMatchLiteral(std::vector<cv::Mat>&, std::vector<Camera>&, std::vector<std::array<int, 2>>&, cv::Mat&, int, double, double);
+void svaSelectDevice(int device);
+std::array<uint8_t, SVA_COMM_ID_BYTES> svaCommUniqueId();
+void svaCommInit(const std::array<uint8_t, SVA_COMM_ID_BYTES>& id, int rank, int world);
+std::vector<uint16_t> svaDepthPairSharded(const sva_params&, cv::Mat&, std::vector<cv::Mat>&, cv::Mat*, int, std::vector<float>*);
+std::vector<uint16_t> svaDepthRowsSharded(const sva_params&, cv::Mat&, std::vector<cv::Mat>&, cv::Mat*, int, int, int*, int*, std::vector<float>*);
 
 static cv::Mat g_mask;
 cv::Mat getFaceMask(cv::Mat&) { return g_mask.clone(); }
@@ -64,5 +71,33 @@ extern "C" long long adapter_depth_consumers(const double* depth, int w, int h, 
         auto groups = getGroups(cameras, "CHESS");
         for (size_t g = 0; g < groups.size() && g < 16; g++) out_group_sizes[g] = (int)groups[g].size();
         return (long long)cloud.size();
+    } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+
+// a C++ host reaching the multi-GPU entry points through the adapter (world_size ranks, one process each; id = 128 bytes from rank 0's
+// adapter_comm_id, distributed by the launcher): pair-sharded frame (map on rank 0) and row-sharded frame (this rank's rows)
+extern "C" int adapter_comm_id(uint8_t* out128) {
+    try { auto id = svaCommUniqueId(); std::memcpy(out128, id.data(), id.size()); return 0; } catch (const std::exception& e) { g_err = e.what(); return -1; }
+}
+extern "C" int adapter_multi_gpu(int device, const uint8_t* id128, int rank, int world, const sva_params* p, const uint8_t* ref, const uint8_t* const* others,
+                                 uint16_t* out_pairs_disp, uint16_t* out_rows_disp, float* out_rows_sub, int* out_y0, int* out_rows) {
+    try {
+        svaSelectDevice(device);
+        std::array<uint8_t, SVA_COMM_ID_BYTES> id;
+        std::memcpy(id.data(), id128, id.size());
+        static bool inited = false;
+        if (!inited) { svaCommInit(id, rank, world); inited = true; }
+        const int w = p->width, h = p->height;
+        cv::Mat r(h, w, CV_8UC1);
+        std::memcpy(r.data, ref, (size_t)w * h);
+        std::vector<cv::Mat> o;
+        for (int i = 0; i < p->n_pairs; i++) { cv::Mat m(h, w, CV_8UC1); std::memcpy(m.data, others[i], (size_t)w * h); o.push_back(m); }
+        std::vector<uint16_t> d = svaDepthPairSharded(*p, r, o, nullptr, 0, nullptr);
+        if (rank == 0) std::memcpy(out_pairs_disp, d.data(), d.size() * 2);
+        std::vector<float> sub;
+        std::vector<uint16_t> dr = svaDepthRowsSharded(*p, r, o, nullptr, rank, world, out_y0, out_rows, &sub);
+        std::memcpy(out_rows_disp, dr.data(), dr.size() * 2);
+        std::memcpy(out_rows_sub, sub.data(), sub.size() * 4);
+        return 0;
     } catch (const std::exception& e) { g_err = e.what(); return -1; }
 }

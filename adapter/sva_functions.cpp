@@ -20,10 +20,11 @@
 
 namespace {
 
+int g_device = 0;  // svaSelectDevice: one process per GPU picks its GPU before the first call
 sva_ctx* ctx() {  // one context per process (the reference is single-threaded, functions.h has no handle argument)
     static sva_ctx* c = nullptr;
     if (!c) {
-        int rc = sva_create(0, &c);
+        int rc = sva_create(g_device, &c);
         if (rc != SVA_OK) throw cv::Exception(std::string("sva_create failed: a B200 GPU is required (status ") + std::to_string(rc) + ")");
     }
     return c;
@@ -165,4 +166,51 @@ std::vector<std::vector<std::array<int, 2>>> getGroups(std::vector<Camera>& came
         groups.push_back(grp);
     }
     return groups;
+}
+
+// ---- one frame over several GPUs (one process per GPU; any launcher — mpirun, torchrun, a shell loop — provides rank and world) ----
+// No reference counterpart (the reference is one thread): the sharding units are its pair loop (src/CameraStereoVision.cpp:55) and its
+// pixel-row loop (:49).  Rank 0 calls svaCommUniqueId() and hands the 128 bytes to the others by whatever channel the launcher offers;
+// every rank then calls svaCommInit (collective).  Volume-mode parameters are the C ABI's sva_params.
+void svaSelectDevice(int device) { g_device = device; }
+std::array<uint8_t, SVA_COMM_ID_BYTES> svaCommUniqueId() {
+    std::array<uint8_t, SVA_COMM_ID_BYTES> id{};
+    if (sva_comm_get_unique_id(id.data()) != SVA_OK) throw cv::Exception("svaCommUniqueId: libnccl.so.2 could not be loaded");
+    return id;
+}
+void svaCommInit(const std::array<uint8_t, SVA_COMM_ID_BYTES>& id, int rank, int world) { check(sva_comm_init(ctx(), id.data(), rank, world), "svaCommInit"); }
+// camera pairs sharded over the ranks, packed NCCL reduce of the AD volume onto `root` (north_star's scheme): the u16 disparity map
+// (rows * cols; SVA_DISP_INVALID where rejected) on root, empty elsewhere
+std::vector<uint16_t> svaDepthPairSharded(const sva_params& p, cv::Mat& ref, std::vector<cv::Mat>& others, cv::Mat* mask, int root, std::vector<float>* subpix) {
+    std::vector<sva_image_u8> o;
+    for (auto& m : others) o.push_back(view(m));
+    sva_image_u8 r = view(ref), mk = mask ? view(*mask) : sva_image_u8{};
+    std::vector<uint16_t> disp((size_t)p.width * p.height);
+    std::vector<float> sub((size_t)p.width * p.height);
+    check(sva_depth_pair_sharded(ctx(), &p, &r, o.data(), mask ? &mk : nullptr, root, disp.data(), sub.data()), "svaDepthPairSharded");
+    if (subpix) *subpix = sub;
+    return disp;
+}
+// image rows sharded over the ranks, path-line state handed from GPU to GPU by peer-direct stores (sva_rows_*): this rank's rows
+// [y0, y0 + rows) of the map.  The first call for a geometry opens and connects the link (collective).
+std::vector<uint16_t> svaDepthRowsSharded(const sva_params& p, cv::Mat& ref, std::vector<cv::Mat>& others, cv::Mat* mask, int rank, int world, int* y0, int* rows,
+                                          std::vector<float>* subpix) {
+    static int open_w = 0, open_h = 0, open_d = 0;
+    if (open_w != p.width || open_h != p.height || open_d != p.num_disp) {
+        check(sva_rows_open(ctx(), &p, rank, world), "sva_rows_open");
+        if (world > 1) check(sva_rows_connect_comm(ctx()), "sva_rows_connect_comm");
+        open_w = p.width; open_h = p.height; open_d = p.num_disp;
+    }
+    int32_t by0 = 0, brows = 0;
+    check(sva_rows_block(ctx(), &by0, &brows), "sva_rows_block");
+    std::vector<sva_image_u8> o;
+    for (auto& m : others) o.push_back(view(m));
+    sva_image_u8 r = view(ref), mk = mask ? view(*mask) : sva_image_u8{};
+    std::vector<uint16_t> disp((size_t)p.width * brows);
+    std::vector<float> sub((size_t)p.width * brows);
+    check(sva_depth_rows_sharded(ctx(), &p, &r, o.data(), mask ? &mk : nullptr, disp.data(), sub.data()), "svaDepthRowsSharded");
+    if (y0) *y0 = by0;
+    if (rows) *rows = brows;
+    if (subpix) *subpix = sub;
+    return disp;
 }

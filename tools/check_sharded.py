@@ -24,7 +24,7 @@ from stereovisionarray_b200.pipeline import DepthContext  # noqa: E402
 ap = argparse.ArgumentParser()
 ap.add_argument("--c3", action="store_true", help="the full c3 frame against the committed oracle digests")
 ap.add_argument("--time", action="store_true", help="with --c3: device-timed row pipelines")
-ap.add_argument("--schemes", default="pairs,slices,rows,rows_direct")
+ap.add_argument("--schemes", default="pairs,slices,rows,rows_direct,adapter")
 args = ap.parse_args()
 
 rank, local, world = int(os.environ["RANK"]), int(os.environ["LOCAL_RANK"]), int(os.environ["WORLD_SIZE"])
@@ -33,6 +33,7 @@ dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 OFF15 = [(gx, gy) for gy in range(-1, 3) for gx in range(-1, 3) if (gx, gy) != (0, 0)]
 schemes = args.schemes.split(",")
 ok = True
+ADAPTER_UID = None
 
 
 def say(msg):
@@ -76,6 +77,37 @@ def run_schemes(p, sc, tag):
     torch.cuda.synchronize()
     dist.barrier()
     ctx.close()
+    if "adapter" in schemes and not args.c3:
+        # a C++ host's route: adapter/sva_functions.cpp (svaCommInit, svaDepthPairSharded, svaDepthRowsSharded) through its C test glue
+        import ctypes as C
+        so = os.path.join(ROOT, "adapter", "_build", "libsva_adapter_test.so")
+        if os.path.exists(so):
+            sys.path.insert(0, os.path.join(ROOT, "tests"))
+            from test_gpu_adapter import adapter_multi_gpu
+            lib = C.CDLL(so)
+            lib.adapter_last_error.restype = C.c_char_p
+            uid = [None]
+            if rank == 0:
+                buf = (C.c_uint8 * 128)()
+                assert lib.adapter_comm_id(buf) == 0
+                uid = [bytes(buf)]
+            global ADAPTER_UID
+            if ADAPTER_UID is None:  # the adapter holds ONE communicator per process
+                dist.broadcast_object_list(uid, src=0)
+                ADAPTER_UID = uid[0]
+            dp, dr, sr, y0 = adapter_multi_gpu(lib, local, ADAPTER_UID, rank, world, p, sc["ref"], sc["others"])
+            rows_per = sdist.row_blocks(p.height, world)[0]
+            d_t = torch.full((rows_per, p.width), abi.SVA_DISP_INVALID, dtype=torch.int32, device="cuda")
+            s_t = torch.full((rows_per, p.width), -1.0, dtype=torch.float32, device="cuda")
+            d_t[:dr.shape[0]] = torch.from_numpy(dr.astype(np.int32)).cuda()
+            s_t[:dr.shape[0]] = torch.from_numpy(sr).cuda()
+            d_all = [torch.empty_like(d_t) for _ in range(world)] if rank == 0 else None
+            s_all = [torch.empty_like(s_t) for _ in range(world)] if rank == 0 else None
+            dist.gather(d_t, d_all, dst=0)
+            dist.gather(s_t, s_all, dst=0)
+            if rank == 0:
+                out["adapter_rows"] = (torch.cat(d_all)[:p.height].cpu().numpy().astype(np.uint16), torch.cat(s_all)[:p.height].cpu().numpy())
+                out["adapter_pairs"] = (dp, out["adapter_rows"][1])  # the pair-sharded wrapper returns the integer map
     return out
 
 
@@ -87,8 +119,10 @@ if not args.c3:
         out = run_schemes(p, sc, "%dx%dx%d" % (w, h, D))
         if rank == 0:
             d0, s0 = Oracle().depth_from_array(p, sc["ref"], sc["others"], sc["mask"])
+            d0n, s0n = Oracle().depth_from_array(p, sc["ref"], sc["others"], None) if any(k.startswith("adapter") for k in out) else (None, None)
             for name, o in out.items():
-                same = np.array_equal(o[0], d0) and np.array_equal(o[1], s0)
+                dref, sref = (d0n, s0n) if name.startswith("adapter") else (d0, s0)  # the adapter's test glue passes no mask
+                same = np.array_equal(o[0], dref) and np.array_equal(o[1], sref)
                 say("%s %dx%dx%d over %d GPUs vs oracle: %s (valid %.3f)" % (name, w, h, D, world, "bit-exact" if same else "MISMATCH", float((d0 != 0xFFFF).mean())))
                 ok = ok and same
 else:
