@@ -453,8 +453,8 @@ def run_c3(args, R, headline=False):
         res = dict(base, **run_c3_host_sequenced(args, R, p, sc, steps))
         launches = res.pop("launches")
     else:
-        in_flight = 3
-        ctxs = [DepthContext(R.local_rank) for _ in range(in_flight)]
+        max_in_flight = 3
+        ctxs = [DepthContext(R.local_rank) for _ in range(max_in_flight)]
         try:
             for c in ctxs:
                 c.upload(p, sc["ref"], sc["others"], sc["mask"])
@@ -473,16 +473,23 @@ def run_c3(args, R, headline=False):
                 ctxs[0].rows_download()  # checks the hand-off time-outs
             lat /= steps
             launches = (ctxs[0].launches() - l0) // steps
-            frames = 4 * in_flight
+            # frames back to back with 1, 2, 3 contexts (= frames in flight) per GPU: with few GPUs every rank is busy all the time and one
+            # context is best; with many, the sweeps of consecutive frames fill each other's pipeline bubbles
+            by_in_flight = {}
+            for in_flight in range(1, max_in_flight + 1):
+                frames = 12
+                use = ctxs[:in_flight]
+                R.barrier()
+                for c in use:
+                    c.timer_start()
+                for i in range(frames):
+                    use[i % in_flight].rows_run()
+                by_in_flight[in_flight] = R.max(max(c.timer_stop() for c in use)) / frames
+                for c in use:
+                    c.rows_download()
             R.barrier()
-            for c in ctxs:
-                c.timer_start()
-            for i in range(frames):
-                ctxs[i % in_flight].rows_run()
-            thr = R.max(max(c.timer_stop() for c in ctxs)) / frames
-            for c in ctxs:
-                c.rows_download()
-            R.barrier()
+            in_flight = min(by_in_flight, key=by_in_flight.get)
+            thr = by_in_flight[in_flight]
         finally:
             for c in ctxs:
                 c.close()
@@ -491,6 +498,7 @@ def run_c3(args, R, headline=False):
                                 "%.1f MB of path state straight into the next GPU's memory (CUDA IPC over NVLink), sequenced by device flags; no volume collective, no NCCL on the data path"
                                 % (blocks, 3 * p.width * p.num_disp * 2 / 1e6),
                    latency_ms=round(lat, 3), latency_value=round(mde / (lat / 1e3), 1), in_flight=in_flight, ms_per_frame=round(thr, 3), frames_per_s=round(1e3 / thr, 2),
+                   ms_per_frame_by_in_flight={str(k): round(v, 3) for k, v in by_in_flight.items()},
                    value=round(mde / (thr / 1e3), 1), parity="tools/check_sharded.py --c3: bit-exact against the oracle digests (profiles/)")
     if not headline:
         return res

@@ -13,8 +13,7 @@
 //
 // A CTA = 8 rows x 128 columns x 32 disparities.  The views live in HBM as zero-bordered, 16-byte-pitched copies (out-of-image
 // source = 0 = the spec's OOB value, so there are no bounds checks); the part of every view that the tile's disparity range can
-// touch is staged once per CTA with 16-byte cp.async row copies, in groups of pairs that alternate between two buffers so that the next
-// group streams in while the current one is accumulated.  The integer ALU pipe is the bound (B200: 64 int lanes per SM).
+// touch is staged once per CTA with 16-byte cp.async row copies.  The integer ALU pipe is the bound (B200: 64 int lanes per SM).
 #include <algorithm>
 #include <cstdlib>
 
@@ -25,7 +24,7 @@
 #define AD2_DR 32
 #define AD2_THREADS 512
 #define AD2_MAXG 2
-#define AD2_GROUP_BUDGET (28 * 1024)  // per staging buffer; two buffers per CTA, two CTAs per SM
+#define AD2_SMEM_BUDGET (96 * 1024)
 
 __host__ __device__ constexpr int ad2_sp(int agx) { return agx == 0 ? 160 : (agx == 1 ? 192 : 224); }  // staged row pitch, bytes
 __host__ __device__ constexpr int ad2_rows(int agy) { return AD2_TH + (AD2_DR - 1) * agy; }
@@ -41,8 +40,7 @@ struct Ad2Params {
     int n;                              // pairs handled by this launch
     int8_t gx[SVA_MAX_PAIRS], gy[SVA_MAX_PAIRS], phi[SVA_MAX_PAIRS];
     uint8_t img[SVA_MAX_PAIRS];         // index of the pair's view in imgs
-    int ngroups;                        // pairs are staged in groups of at most group_bytes, double-buffered (two buffers of group_bytes)
-    int group_bytes;
+    int ngroups;                        // pairs are staged in groups that fit the shared-memory budget
     uint8_t gbeg[SVA_MAX_PAIRS + 1];
     int ty0;                            // first tile row of this launch (row-block pipeline; 0 for a whole frame)
 };
@@ -91,49 +89,40 @@ k_ad_tile(const Ad2Params q) {
     for (int i = 0; i < 16; i++) { ae[i] = 0; ao[i] = 0; }
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(ad2_smem);
 
-    // ---- geometry of every pair's staged rectangle, once: one thread per pair.  Groups alternate between two staging buffers. ----
-    if (t < q.n) {
-        const int k = t;
-        int g = 0;
-        while (k >= q.gbeg[g + 1]) g++;
-        const int gx = q.gx[k], gy = q.gy[k];
-        int soff = (g & 1) * q.group_bytes;
-        for (int j = q.gbeg[g]; j < k; j++) soff += ad2_rows(q.gy[j] < 0 ? -q.gy[j] : q.gy[j]) * ad2_sp(q.gx[j] < 0 ? -q.gx[j] : q.gx[j]);
-        const int sp = ad2_sp(gx < 0 ? -gx : gx), rows = ad2_rows(gy < 0 ? -gy : gy);
-        // first staged row / column in view coordinates (disparity index AD2_DR-1 reaches furthest towards -g)
-        const int ylo = y0 - gy * (q.dmin + da) - (gy > 0 ? (AD2_DR - 1) * gy : 0);
-        const int v = q.padx + q.phi[k] + x0 - gx * (q.dmin + da) - (gx > 0 ? (AD2_DR - 1) * gx : 0);
-        const int c0 = v & ~15, e = v - c0;
-        s_off[k] = soff + (gx > 0 ? (AD2_DR - 1) * gx : 0) + e + (gy > 0 ? (AD2_DR - 1) * gy : 0) * sp;
-        s_src[k] = q.imgs + (size_t)q.img[k] * q.img_bytes + (size_t)(q.pady + ylo) * q.pp + c0;
-        s_geo[k] = make_int4(soff, sp, rows, 0);
-    }
-    __syncthreads();
-    // stage group g: thread (tr, tc) copies 16-byte chunk tc of rows tr, tr + 32, ... of every pair of the group (asynchronous)
-    auto stage = [&](const int g) {
-        const int tc16 = (t & 15) * 16, tr = t >> 4;
-        for (int k = q.gbeg[g]; k < q.gbeg[g + 1]; k++) {
-            const int4 geo = s_geo[k];  // dst offset, pitch, rows
-            if (tc16 < geo.y) {
-                const uint8_t* src = s_src[k] + tc16 + (size_t)tr * q.pp;
-                uint32_t dst = smem_base + geo.x + tc16 + tr * geo.y;
-                for (int rr = tr; rr < geo.z; rr += AD2_THREADS / 16) {
-                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
-                    src += (size_t)(AD2_THREADS / 16) * q.pp; dst += (AD2_THREADS / 16) * geo.y;
-                }
-            }
-        }
-        asm volatile("cp.async.commit_group;" ::: "memory");
-    };
-    stage(0);
     for (int g = 0; g < q.ngroups; g++) {
         const int kb = q.gbeg[g], ke = q.gbeg[g + 1];
-        // double buffering: the next group's views stream in while this group is accumulated (its buffer was released by the barrier
-        // that ended group g - 1)
-        if (g + 1 < q.ngroups) {
-            stage(g + 1);
-            asm volatile("cp.async.wait_group 1;" ::: "memory");
-        } else {
+        if (g > 0) __syncthreads();  // everyone is done reading the previous group's tiles
+        // ---- stage: one thread per pair works out the pair's rectangle; then thread (tr, tc) copies 16-byte chunk tc of rows
+        // tr, tr + 32, ... of every pair of the group ----
+        if (t < ke - kb) {
+            const int k = kb + t;
+            const int gx = q.gx[k], gy = q.gy[k];
+            int soff = 0;
+            for (int j = kb; j < k; j++) soff += ad2_rows(q.gy[j] < 0 ? -q.gy[j] : q.gy[j]) * ad2_sp(q.gx[j] < 0 ? -q.gx[j] : q.gx[j]);
+            const int sp = ad2_sp(gx < 0 ? -gx : gx), rows = ad2_rows(gy < 0 ? -gy : gy);
+            // first staged row / column in view coordinates (disparity index AD2_DR-1 reaches furthest towards -g)
+            const int ylo = y0 - gy * (q.dmin + da) - (gy > 0 ? (AD2_DR - 1) * gy : 0);
+            const int v = q.padx + q.phi[k] + x0 - gx * (q.dmin + da) - (gx > 0 ? (AD2_DR - 1) * gx : 0);
+            const int c0 = v & ~15, e = v - c0;
+            s_off[k] = soff + (gx > 0 ? (AD2_DR - 1) * gx : 0) + e + (gy > 0 ? (AD2_DR - 1) * gy : 0) * sp;
+            s_src[k] = q.imgs + (size_t)q.img[k] * q.img_bytes + (size_t)(q.pady + ylo) * q.pp + c0;
+            s_geo[k] = make_int4(soff, sp, rows, 0);
+        }
+        __syncthreads();
+        {
+            const int tc16 = (t & 15) * 16, tr = t >> 4;
+            for (int k = kb; k < ke; k++) {
+                const int4 geo = s_geo[k];  // dst offset, pitch, rows
+                if (tc16 < geo.y) {
+                    const uint8_t* src = s_src[k] + tc16 + (size_t)tr * q.pp;
+                    uint32_t dst = smem_base + geo.x + tc16 + tr * geo.y;
+                    for (int rr = tr; rr < geo.z; rr += AD2_THREADS / 16) {
+                        asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst), "l"(src) : "memory");
+                        src += (size_t)(AD2_THREADS / 16) * q.pp; dst += (AD2_THREADS / 16) * geo.y;
+                    }
+                }
+            }
+            asm volatile("cp.async.commit_group;" ::: "memory");
             asm volatile("cp.async.wait_group 0;" ::: "memory");
         }
         __syncthreads();
@@ -152,7 +141,6 @@ k_ad_tile(const Ad2Params q) {
                 default: ad2_pair_gy<2>(gy, bp, r, ae, ao); break;
             }
         }
-        if (g + 2 < q.ngroups) __syncthreads();  // everyone is done with this buffer before group g + 2 streams into it
     }
     // ---- store: per disparity pair one 16-byte run of 4 columns in its plane ----
     const int d0 = da + 16 * sub;
@@ -240,7 +228,7 @@ int sva_run_ad2(sva_ctx* ctx) {
         q.gx[i] = (int8_t)p.pair_gx[k]; q.gy[i] = (int8_t)p.pair_gy[k]; q.img[i] = (uint8_t)k;
         q.phi[i] = (int8_t)(((p.pair_gx[k] * p.min_disp) % 4 + 4) % 4);
         const size_t bytes = (size_t)ad2_rows(abs(p.pair_gy[k])) * ad2_sp(abs(p.pair_gx[k]));
-        if (group_bytes + bytes > AD2_GROUP_BUDGET && group_bytes > 0) { q.gbeg[++q.ngroups] = (uint8_t)i; group_bytes = 0; }
+        if (group_bytes + bytes > AD2_SMEM_BUDGET && group_bytes > 0) { q.gbeg[++q.ngroups] = (uint8_t)i; group_bytes = 0; }
         group_bytes += bytes;
         max_group = std::max(max_group, group_bytes);
     }
@@ -250,8 +238,7 @@ int sva_run_ad2(sva_ctx* ctx) {
         ctx->have_ad = true;
         return SVA_OK;
     }
-    q.group_bytes = (int)((max_group + 15) & ~(size_t)15);
-    const size_t smem = 2 * (size_t)q.group_bytes + 16;
+    const size_t smem = max_group + 16;
     SVA_CUDA_OK(ctx, cudaFuncSetAttribute(k_ad_tile, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(ctx, "k_ad_tile");

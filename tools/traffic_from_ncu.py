@@ -1,6 +1,6 @@
 """ncu --set full capture of ONE frame (tools/profile_frame.py --iters 1 under `ncu --set full -k regex:k_ ...`) -> profiles/traffic.json.
 
-    python tools/traffic_from_ncu.py <capture.ncu-rep> <config key, e.g. c1_k20> [--last N]
+    python tools/traffic_from_ncu.py <capture.ncu-rep> <config key, e.g. c1_k20> [--last N] [--out file.json]
 
 For every launch of the LAST frame in the capture (N launches; default: all), in launch order: the kernel symbol, measured DRAM bytes
 (dram__bytes_read.sum + dram__bytes_write.sum), duration under ncu, and the utilisation of the units that can bound it.  `bound` is the
@@ -58,7 +58,7 @@ def main():
     recs = records(path)
     if "--last" in sys.argv:
         recs = recs[-int(sys.argv[sys.argv.index("--last") + 1]):]
-    tj = os.path.join(ROOT, "profiles", "traffic.json")
+    tj = sys.argv[sys.argv.index("--out") + 1] if "--out" in sys.argv else os.path.join(ROOT, "profiles", "traffic.json")
     try:
         with open(tj) as f:
             data = json.load(f)
