@@ -456,6 +456,8 @@ def run_c3(args, R, headline=False):
         max_in_flight = 3
         ctxs = [DepthContext(R.local_rank) for _ in range(max_in_flight)]
         try:
+            for c in ctxs[1:]:  # ONE stream for all of them: frames are interleaved by enqueue order, never by concurrent kernels
+                c.set_stream(ctxs[0].get_stream())
             for c in ctxs:
                 c.upload(p, sc["ref"], sc["others"], sc["mask"])
                 sdist.rows_direct_connect(c, p, rank, world)
@@ -473,18 +475,20 @@ def run_c3(args, R, headline=False):
                 ctxs[0].rows_download()  # checks the hand-off time-outs
             lat /= steps
             launches = (ctxs[0].launches() - l0) // steps
-            # frames back to back with 1, 2, 3 contexts (= frames in flight) per GPU: with few GPUs every rank is busy all the time and one
-            # context is best; with many, the sweeps of consecutive frames fill each other's pipeline bubbles
+            # frames back to back with P = 1, 2, 3 frames in flight per GPU (P contexts on one stream): phase 0 of frame f is enqueued before
+            # phase 1 of frame f - P + 1, so a rank spends the wait for the far end of its second sweep on the next frames' first halves
             by_in_flight = {}
             for in_flight in range(1, max_in_flight + 1):
                 frames = 12
                 use = ctxs[:in_flight]
                 R.barrier()
-                for c in use:
-                    c.timer_start()
-                for i in range(frames):
-                    use[i % in_flight].rows_run()
-                by_in_flight[in_flight] = R.max(max(c.timer_stop() for c in use)) / frames
+                ctxs[0].timer_start()
+                for f in range(frames + in_flight - 1):
+                    if f < frames:
+                        use[f % in_flight].rows_run_phase(0)
+                    if f - in_flight + 1 >= 0:
+                        use[(f - in_flight + 1) % in_flight].rows_run_phase(1)
+                by_in_flight[in_flight] = R.max(ctxs[0].timer_stop()) / frames
                 for c in use:
                     c.rows_download()
             R.barrier()

@@ -92,6 +92,7 @@ const char* sva_last_error(const sva_ctx* ctx);      /* valid until the next cal
 int sva_api_version(void);
 int sva_set_stream(sva_ctx* ctx, void* cuda_stream); /* run on a caller stream (e.g. torch's; NULL = the legacy default stream) */
 int sva_use_own_stream(sva_ctx* ctx);                 /* back to the ctx's own non-blocking stream */
+int sva_get_stream(sva_ctx* ctx, void** out_cuda_stream);  /* the stream the ctx currently runs on (to share it with another ctx) */
 int sva_synchronize(sva_ctx* ctx);
 int sva_kernel_launches(const sva_ctx* ctx, uint64_t* out_count); /* kernels launched by this ctx so far */
 /* Self-check for boxes without compute-sanitizer: device buffers allocated after sva_debug_set_guard(ctx, 1) carry 256 KiB canary bands
@@ -282,6 +283,10 @@ int sva_rows_connect_comm(sva_ctx* ctx);
 int sva_rows_connect_local(sva_ctx* ctx, sva_ctx* prev, sva_ctx* next);
 int sva_rows_block(const sva_ctx* ctx, int32_t* out_y0, int32_t* out_rows);
 int sva_rows_run(sva_ctx* ctx);
+/* The same frame in two parts (phase 0: cost volume, horizontal paths, the sweep that reaches this rank first; phase 1: the other sweep and
+ * K3), for hosts that keep several frames in flight: several contexts share ONE stream (sva_get_stream / sva_set_stream) and the host
+ * enqueues phase 0 of frame f, then phase 1 of frame f - P + 1 — frames overlap across GPUs without two big kernels ever running at once. */
+int sva_rows_run_phase(sva_ctx* ctx, int32_t phase);
 int sva_rows_download(sva_ctx* ctx, uint16_t* out_disp_rows, float* out_subpix_rows);  /* the block's rows; out_subpix_rows may be NULL */
 int sva_rows_close(sva_ctx* ctx);
 /* one synchronous call per frame: upload + sva_rows_run + sva_rows_download */

@@ -223,6 +223,7 @@ struct BoxPParams {
 __global__ void __launch_bounds__(256, 2)
 k_box_planar(BoxPParams q) {
     __shared__ __align__(16) uint32_t s_out[2][BXP_WARPS][BXP_OPITCH];
+    __shared__ __align__(8) unsigned long long s_bar[2];  // one mbarrier per staging buffer: "all 8 warps have written this row's words"
     __shared__ uint2 s_T[BXP_WARPS][8 * BXP_TCOLS];
     __shared__ int s_limy[BXP_MAX_BAND];
     const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
@@ -241,6 +242,11 @@ k_box_planar(BoxPParams q) {
     }
     uint2* tbl = &s_T[warp][8 + lane];
     if (lane == 0) tbl[0] = make_uint2(0u, 0u);  // T[0] = 0 (never overwritten)
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(BXP_WARPS) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8), "r"(BXP_WARPS) : "memory");
+    }
     int offh[8], offl[8];
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -267,6 +273,23 @@ k_box_planar(BoxPParams q) {
     const size_t orow = (size_t)W * D;
     const uint32_t kB = (uint32_t)k << 16;
 
+    // transposed store of output row r (all 8 warps' words of that row are in s_out[r & 1] once the barrier's phase r >> 1 has completed)
+    auto store_row = [&](const int r) {
+        const uint32_t bar = bar0 + 8 * (r & 1), parity = (uint32_t)(r >> 1) & 1u;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "BOXWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra BOXDONE_%=;\n"
+            "bra BOXWAIT_%=;\n"
+            "BOXDONE_%=:\n"
+            "}" ::"r"(bar), "r"(parity) : "memory");
+        const uint32_t* src = &s_out[r & 1][4 * hf][xl0];
+        if (st0) *reinterpret_cast<uint4*>(po) = make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]);
+        if (st1) *reinterpret_cast<uint4*>(po + 128 * D) = make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]);
+        po += orow;
+    };
     // one update + (once the window is full) one output row; cur = this row's words, the caller keeps the next row's loads in flight
     auto row = [&](const int n, const uint4& e0, const uint4& e1, const uint4& l0, const uint4& l1) {
         {
@@ -323,14 +346,17 @@ k_box_planar(BoxPParams q) {
                 w[j] = c1 * 65536u + c0;
             }
         }
+        // The 8 warps meet through a SPLIT barrier instead of __syncthreads: a warp announces its words of row `it` (mbarrier arrive) and
+        // goes on; the transposed store of a row happens one row later, when that row's barrier phase has completed — so a warp only
+        // ever waits for the others' PREVIOUS row, and the warps of a CTA drift up to a row apart instead of marching in phase through
+        // the same pipes.  WAR on the double buffer: whoever writes buffer b for row it + 2 has passed the wait for row it + 1, i.e.
+        // every warp has arrived for row it + 1, which each does after its store pass of row it.
+        if (it > 0) store_row(it - 1);
         uint32_t* so = &s_out[it & 1][warp][lane * 8];
         *reinterpret_cast<uint4*>(so) = make_uint4(w[0], w[1], w[2], w[3]);
         *reinterpret_cast<uint4*>(so + 4) = make_uint4(w[4], w[5], w[6], w[7]);
-        __syncthreads();  // one barrier per row: s_out is double-buffered
-        const uint32_t* src = &s_out[it & 1][4 * hf][xl0];
-        if (st0) *reinterpret_cast<uint4*>(po) = make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]);
-        if (st1) *reinterpret_cast<uint4*>(po + 128 * D) = make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]);
-        po += orow;
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (it & 1)) : "memory");
     };
 
     // software pipeline, unrolled by two so the row buffers ping-pong without register moves
@@ -351,6 +377,7 @@ k_box_planar(BoxPParams q) {
         fetch(n + 2, a0, a1, al0, al1);
         row(n + 1, b0, b1, bl0, bl1);
     }
+    store_row(y1 - y0 - 1);  // the last row's deferred store
 }
 
 int sva_ap_prepare(sva_ctx* ctx);

@@ -147,6 +147,12 @@ int sva_use_own_stream(sva_ctx* c) {
     return SVA_OK;
 }
 
+int sva_get_stream(sva_ctx* c, void** out) {
+    if (!c || !out) return SVA_ERR_BAD_ARG;
+    *out = (void*)c->stream;
+    return SVA_OK;
+}
+
 int sva_synchronize(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));

@@ -75,6 +75,7 @@ struct RowsLink {
     uint8_t* next = nullptr;
     bool prev_ipc = false, next_ipc = false;
     uint32_t seq = 0;              // frames enqueued so far
+    int phase_done = 1;            // phases of frame `seq` enqueued so far (0: none yet, 1: both / first only — see sva_rows_run_phase)
     long long timeout_ns = 20000LL * 1000000LL;
     uint32_t* flag(uint8_t* base, int i) const { return (uint32_t*)(base + (size_t)i * FLAG_STRIDE); }
     uint16_t* d_in(uint8_t* base) const { return (uint16_t*)(base + FLAGS_BYTES); }
@@ -331,6 +332,8 @@ int sva_rows_connect_local(sva_ctx* c, sva_ctx* prev, sva_ctx* next) {
     return SVA_OK;
 }
 
+int sva_rows_run_phase(sva_ctx* c, int32_t phase);
+
 int sva_rows_block(const sva_ctx* c, int32_t* out_y0, int32_t* out_rows) {
     if (!c || !c->rows_link || !out_y0 || !out_rows) return SVA_ERR_BAD_ARG;
     const RowsLink* l = (const RowsLink*)c->rows_link;
@@ -339,9 +342,21 @@ int sva_rows_block(const sva_ctx* c, int32_t* out_y0, int32_t* out_rows) {
 }
 
 int sva_rows_run(sva_ctx* c) {
+    SVA_TRY(sva_rows_run_phase(c, 0));
+    return sva_rows_run_phase(c, 1);
+}
+
+// One frame in two parts, so that a host with several contexts ON ONE STREAM can interleave frames without ever running two of the big
+// kernels at once (concurrent launches break the resident, paced waves of the SGM marches: measured 2.5x slower):
+//   phase 0 = cost volume of the block, horizontal paths, and the sweep that reaches this rank first;  phase 1 = the other sweep and K3.
+// Enqueue order for P frames in flight: phase 0 of frame f, then phase 1 of frame f - P + 1 — the wait for the far end of the second
+// sweep's chain is then spent computing the next frames' phase 0.
+int sva_rows_run_phase(sva_ctx* c, int32_t phase) {
     if (!c) return SVA_ERR_BAD_ARG;
     RowsLink* l = (RowsLink*)c->rows_link;
     if (!l) return c->fail(SVA_ERR_STATE, "rows_run: sva_rows_open first");
+    if (phase != 0 && phase != 1) return c->fail(SVA_ERR_BAD_ARG, "rows_run_phase: phase must be 0 or 1");
+    if (phase == 0 ? l->phase_done != 1 : l->phase_done != 0) return c->fail(SVA_ERR_STATE, "rows_run_phase: phases of a frame run in order 0, 1");
     if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
     const sva_params& p = c->prm;
     if (p.width != l->W || p.height != l->H || p.num_disp != l->D || p.n_paths != 8) return c->fail(SVA_ERR_STATE, "rows_run: the uploaded frame does not match the geometry of sva_rows_open");
@@ -350,12 +365,15 @@ int sva_rows_run(sva_ctx* c) {
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
     nvtxRangePushA("sva:rows_block");
     struct Pop { ~Pop() { nvtxRangePop(); } } pop;
-    const uint32_t seq = ++l->seq;
+    const uint32_t seq = phase == 0 ? ++l->seq : l->seq;
+    l->phase_done = phase;
     const int y0 = l->y0, n = l->rows;
     uint32_t* err = l->flag(l->mem, F_ERR);
-    SVA_TRY(sva_frame_rows_begin(c, y0, n));
-    SVA_TRY(sva_frame_run(c, SVA_STAGE_AD));
-    SVA_TRY(sva_frame_run(c, SVA_STAGE_BOX));
+    if (phase == 0) {
+        SVA_TRY(sva_frame_rows_begin(c, y0, n));
+        SVA_TRY(sva_frame_run(c, SVA_STAGE_AD));
+        SVA_TRY(sva_frame_run(c, SVA_STAGE_BOX));
+    }
     auto wait = [&](int f, uint32_t want) -> int {
         c->launches++;
         k_rows_wait<<<1, 1, 0, c->stream>>>(l->flag(l->mem, f), want, l->timeout_ns, err);
@@ -387,9 +405,12 @@ int sva_rows_run(sva_ctx* c) {
     // two ranks that START a sweep do so right after their cost volume and run their horizontal paths afterwards, off the chain.
     const bool starts_chain = G > 1 && (r == 0 || r == G - 1);
     const bool down_first = r < (G + 1) / 2;
-    if (!starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
-    SVA_TRY(sweep(down_first));
-    if (starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
+    if (phase == 0) {
+        if (!starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
+        SVA_TRY(sweep(down_first));
+        if (starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
+        return SVA_OK;
+    }
     SVA_TRY(sweep(!down_first));
     return sva_frame_wta_rows(c, nullptr, y0, n);
 }

@@ -245,6 +245,15 @@ class DepthContext:
         """enqueue this rank's block of the uploaded frame (asynchronous)"""
         check(self._h, self._L.sva_rows_run(self._h))
 
+    def rows_run_phase(self, phase):
+        """phase 0: cost volume, horizontal paths, first sweep; phase 1: second sweep + K3 (see sva_rows_run_phase)"""
+        check(self._h, self._L.sva_rows_run_phase(self._h, int(phase)))
+
+    def get_stream(self):
+        s = C.c_void_p()
+        check(self._h, self._L.sva_get_stream(self._h, C.byref(s)))
+        return s.value or 0
+
     def rows_download(self):
         y0, n = self.rows_block()
         disp = np.empty((n, self.params.width), np.uint16)

@@ -117,3 +117,46 @@ def test_two_gpus_every_scheme_against_the_oracle():
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     lines = [l for l in r.stdout.splitlines() if "vs oracle" in l]
     assert len(lines) >= 9 and all("bit-exact" in l for l in lines), r.stdout
+
+
+def test_rows_direct_frames_in_flight_on_one_stream(oracle):
+    """several frames in flight without concurrent kernels: every rank has P = 2 contexts (own links, own volumes) on ONE stream, and the host
+    enqueues phase 0 of frame f before phase 1 of frame f - 1 (sva_rows_run_phase).  G = 3 local ranks, four frames through the pipeline."""
+    from stereovisionarray_b200.pipeline import DepthContext
+    h, w, D, G, P = 70, 120, 64, 3, 2
+    inputs = [synth.make_scene(h, w, D, OFF8, 1700 + i, face=(i == 1)) for i in range(P)]
+    p = abi.make_params(w, h, D, OFF8, win_half=4, n_paths=8, lr_gx=-1)
+    ctxs = [[DepthContext(0) for _ in range(P)] for _ in range(G)]
+    try:
+        for r in range(G):
+            for j in range(1, P):
+                ctxs[r][j].set_stream(ctxs[r][0].get_stream())
+            for j in range(P):
+                ctxs[r][j].upload(p, inputs[j]["ref"], inputs[j]["others"], inputs[j]["mask"])
+                ctxs[r][j].rows_open(p, r, G)
+        for r in range(G):
+            for j in range(P):
+                ctxs[r][j].rows_connect_local(ctxs[r - 1][j] if r > 0 else None, ctxs[r + 1][j] if r < G - 1 else None)
+        for r in range(G):  # allocate every workspace before anything can wait on a neighbour
+            for c in ctxs[r]:
+                y0, n = c.rows_block()
+                c.rows_begin(y0, n); c.run(abi.STAGE_AD); c.run(abi.STAGE_BOX); c.sgm_rows(2, y0, n); c.wta_rows(None, y0, n); c.synchronize()
+        frames = 4
+        for f in range(frames + P - 1):
+            for r in range(G):
+                if f < frames:
+                    ctxs[r][f % P].rows_run_phase(0)
+                if f - P + 1 >= 0:
+                    ctxs[r][(f - P + 1) % P].rows_run_phase(1)
+        for j in range(P):
+            parts = [ctxs[r][j].rows_download() for r in range(G)]
+            disp = np.concatenate([d for d, _ in parts]); sub = np.concatenate([s for _, s in parts])
+            disp_o, sub_o = oracle.depth_from_array(p, inputs[j]["ref"], inputs[j]["others"], inputs[j]["mask"])
+            assert np.array_equal(disp, disp_o) and np.array_equal(sub, sub_o), "frame set %d" % j
+        from stereovisionarray_b200._lib import SvaError
+        with pytest.raises(SvaError, match="order 0, 1"):
+            ctxs[0][0].rows_run_phase(1)
+    finally:
+        for row in ctxs:
+            for c in row:
+                c.close()
