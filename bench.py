@@ -495,7 +495,7 @@ def run_c3(args, R, headline=False):
             in_flight = min(by_in_flight, key=by_in_flight.get)
             thr = by_in_flight[in_flight]
         finally:
-            for c in ctxs:
+            for c in reversed(ctxs):  # the borrowers first: ctxs[0] owns the stream they run on
                 c.close()
         blocks = sdist.row_blocks(p.height, world)[1]
         res = dict(base, scheme="row blocks %s end to end (sva_rows_*): cost volume and horizontal paths local, row-sweeping paths continue across GPUs — each march stores "

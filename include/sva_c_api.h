@@ -90,7 +90,8 @@ int sva_create(int device, sva_ctx** out);          /* one ctx per GPU; owns a s
 int sva_destroy(sva_ctx* ctx);
 const char* sva_last_error(const sva_ctx* ctx);      /* valid until the next call on ctx */
 int sva_api_version(void);
-int sva_set_stream(sva_ctx* ctx, void* cuda_stream); /* run on a caller stream (e.g. torch's; NULL = the legacy default stream) */
+int sva_set_stream(sva_ctx* ctx, void* cuda_stream); /* run on a caller stream (e.g. torch's; NULL = the legacy default stream); the stream must
+                                                       * stay alive until sva_use_own_stream / another sva_set_stream / sva_destroy */
 int sva_use_own_stream(sva_ctx* ctx);                 /* back to the ctx's own non-blocking stream */
 int sva_get_stream(sva_ctx* ctx, void** out_cuda_stream);  /* the stream the ctx currently runs on (to share it with another ctx) */
 int sva_synchronize(sva_ctx* ctx);

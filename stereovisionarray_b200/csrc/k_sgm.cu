@@ -668,6 +668,31 @@ static int launch_row_group(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, 
     const bool pace = ctx->tune_sgm_pace < 0 ? (size_t)q.W * q.D * 4 >= 768 * 1024 : ctx->tune_sgm_pace != 0;
     if (!pace || n * q.W <= cap || q.W > cap || getenv("SVA_SGM_NO_RANGED")) return launch_dirs(ctx, q, nr, false);
     const int launches = div_up(n * q.W, cap), per_launch = div_up(n * q.W, launches);  // equal shares: every launch streams the whole volume once
+    if (q.row_cnt > 0 && !getenv("SVA_SGM_NO_COLSPLIT")) {
+        // A ROW BLOCK is cut by COLUMNS instead: launch j takes, of every direction, the lines that enter the block inside column range j.
+        // A diagonal drifts one column per row, so over a block of B rows the lines of a launch stay within their column range + B columns:
+        // each launch streams ITS columns of C and S once for all three directions, and only the B-column fringe is streamed by two
+        // launches — (1 + B / range) volumes of traffic per group instead of one per launch (c3, 270-row blocks: 1.14 instead of 2).
+        const int W = q.W;
+        const long long t = q.dys[0] > 0 ? q.row_y0 : q.H - 1 - (q.row_y0 + q.row_cnt - 1);  // rows the sweep has crossed before this block
+        for (int j = 0; j < launches; j++) {
+            const int c0 = (int)((long long)W * j / launches), c1 = (int)((long long)W * (j + 1) / launches);
+            SgmParams s = q;
+            s.ranged = 1; s.ndirs = 0;
+            for (int dir = 0; dir < n; dir++) {
+                // column of line x0 after t rows is (x0 + dx * t) mod W, so the lines entering in [c0, c1) are the range starting at (c0 - dx * t) mod W
+                const int lo = (int)((((long long)c0 - (long long)q.dxs[dir] * t) % W + W) % W), len = c1 - c0, first = std::min(len, W - lo);
+                for (int part = 0; part < 2; part++) {
+                    const int a = part == 0 ? lo : 0, cnt = part == 0 ? first : len - first;
+                    if (cnt <= 0) continue;
+                    s.dxs[s.ndirs] = q.dxs[dir]; s.dys[s.ndirs] = q.dys[dir]; s.state_slot[s.ndirs] = q.state_slot[dir];
+                    s.line_lo[s.ndirs] = a; s.line_cnt[s.ndirs] = cnt; s.ndirs++;
+                }
+            }
+            SVA_TRY(launch_dirs(ctx, s, nr, false));
+        }
+        return SVA_OK;
+    }
     int dir = 0, lo = 0;
     while (dir < n) {
         SgmParams s = q;
@@ -682,6 +707,36 @@ static int launch_row_group(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, 
         SVA_TRY(launch_dirs(ctx, s, nr, false));
     }
     return SVA_OK;
+}
+
+// A row-sweeping group of a WHOLE frame that does not fit one resident wave (3 x 3840 lines at c3): the frame is marched in row blocks of
+// about W / 16 rows — the row-block pipeline of the multi-GPU scheme on one GPU, the path-line state handed from block to block through two
+// small buffers — because a block can be cut by columns (launch_row_group above), which a whole frame cannot (its diagonals cross every column).
+static int run_group_in_blocks(sva_ctx* ctx, SgmParams& q, int nr, const int* idx, int n) {
+    const int W = q.W, H = q.H, D = q.D;
+    const int B = std::min(H, std::max(64, W / 16));
+    const int blocks = div_up(H, B);
+    const size_t state = (((size_t)3 * W * D * sizeof(uint16_t)) + 255) & ~(size_t)255;
+    SVA_TRY(ctx->reserve(ctx->sgm_state, 2 * state));
+    uint16_t* buf[2] = {ctx->sgm_state.as<uint16_t>(), (uint16_t*)(ctx->sgm_state.as<uint8_t>() + state)};
+    const bool down = DIRS[idx[0]][1] > 0;
+    for (int b = 0; b < blocks; b++) {
+        const int blk = down ? b : blocks - 1 - b;  // in sweep order
+        SgmParams s = q;
+        s.row_y0 = blk * B; s.row_cnt = std::min(H, s.row_y0 + B) - s.row_y0;
+        s.state_in = b > 0 ? buf[(b + 1) & 1] : nullptr;
+        s.state_out = b + 1 < blocks ? buf[b & 1] : nullptr;
+        for (int i = 0; i < 3; i++) s.state_slot[i] = i;
+        SVA_TRY(launch_row_group(ctx, s, nr, idx, n));
+    }
+    return SVA_OK;
+}
+
+static bool group_needs_blocks(sva_ctx* ctx, const SgmParams& q, int nr, int n) {
+    const size_t ring = (size_t)(SGM_PF + 1) * 32 * 2 * nr * 2 + (ctx->tune_sgm_bulk ? 80 : 0);
+    const int cap = ctx->sm_count * std::min(SGM_WARPS_PER_SM, (int)(SGM_SMEM_PER_SM / ring));
+    const bool pace = ctx->tune_sgm_pace < 0 ? (size_t)q.W * q.D * 4 >= 768 * 1024 : ctx->tune_sgm_pace != 0;
+    return pace && n * q.W > cap && q.W <= cap && !getenv("SVA_SGM_NO_RANGED") && !getenv("SVA_SGM_NO_COLSPLIT") && q.c_ds == 0;
 }
 
 // exactly the directions of dir_mask, one launch each: the first stores, the others RED, so S ends up as their sum
@@ -786,8 +841,10 @@ int sva_run_sgm(sva_ctx* ctx) {
         // row's C and S lines while these are in L2.  The horizontal lines (W steps each, every row in flight at once) cannot share
         // and get their own launch.
         static const int grp[3][3] = {{0, 4, 5}, {1, 6, 7}, {2, 3, -1}};
-        SVA_TRY(launch_row_group(ctx, q, nr, grp[0], 3));
-        SVA_TRY(launch_row_group(ctx, q, nr, grp[1], 3));
+        for (int g = 0; g < 2; g++) {
+            if (group_needs_blocks(ctx, q, nr, 3)) SVA_TRY(run_group_in_blocks(ctx, q, nr, grp[g], 3));
+            else SVA_TRY(launch_row_group(ctx, q, nr, grp[g], 3));
+        }
         set_dirs(q, grp[2], 2);
         SVA_TRY(launch_dirs(ctx, q, nr, false));
     } else {  // 4 paths (or SVA_SGM_SPLIT=0): one launch, directions that sweep the same rows next to each other

@@ -106,7 +106,7 @@ struct sva_ctx {
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
     DevBuf ref_img, other_imgs, lines, mask, A, AP, C, Craw, S, disp, subpix, other_d, scratch, scratch2, pace_buf;
-    DevBuf pad_imgs, pad_ref, comm_scratch, census, tex_img;
+    DevBuf pad_imgs, pad_ref, comm_scratch, census, tex_img, sgm_state;
     unsigned long long tex = 0;  // cudaTextureObject_t over tex_img (K0's source view, k_misc.cu)
     uint64_t tex_key = 0;
     // ---- multi-GPU (sva_dist.cu) ----

@@ -26,7 +26,7 @@ void sva_ctx::release(DevBuf& b) {
 }
 
 void sva_ctx::device_bufs(std::vector<DevBuf*>& out) {
-    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf, &comm_scratch, &census, &tex_img,
+    out = {&ref_img, &other_imgs, &lines, &mask, &A, &AP, &pad_imgs, &pad_ref, &C, &Craw, &S, &disp, &subpix, &other_d, &scratch, &scratch2, &pace_buf, &comm_scratch, &census, &tex_img, &sgm_state,
            &alt.pad_ref, &alt.pad_imgs, &alt.ref_img, &alt.other_imgs, &alt.lines, &alt.mask, &alt.disp, &alt.subpix};
 }
 
@@ -110,7 +110,8 @@ int sva_create(int device, sva_ctx** out) {
 int sva_destroy(sva_ctx* c) {
     if (!c) return SVA_ERR_BAD_ARG;
     cudaSetDevice(c->device);
-    cudaStreamSynchronize(c->stream);
+    if (c->stream == c->own_stream) cudaStreamSynchronize(c->stream);
+    else cudaDeviceSynchronize();  // a borrowed stream (sva_set_stream) may already be gone: never touch its handle here
     sva_dist_release(c);
     if (c->tex) cudaDestroyTextureObject((cudaTextureObject_t)c->tex);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);

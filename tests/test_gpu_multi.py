@@ -158,5 +158,5 @@ def test_rows_direct_frames_in_flight_on_one_stream(oracle):
             ctxs[0][0].rows_run_phase(1)
     finally:
         for row in ctxs:
-            for c in row:
+            for c in reversed(row):  # the borrowers first: row[0] owns the stream they run on
                 c.close()
