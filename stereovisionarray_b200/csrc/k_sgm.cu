@@ -55,6 +55,7 @@ struct SgmParams {
     const uint16_t* state_in;   // [3][W][D] (slot, line, disparity in the lane layout of S); nullptr where the block starts the sweep
     uint16_t* state_out;        // same shape; nullptr where the block ends the sweep
     int state_slot[8];          // slot of direction i of this launch
+    uint32_t elem_bytes;        // sizeof(uint16_t), as a run-time value (see sgm_elem)
 };
 
 // one step of the recurrence for this lane's 2*NR disparities; L holds L(q,.) on entry and L(p,.) on exit
@@ -125,6 +126,15 @@ template <int NR, int PF, int BULK> __host__ __device__ constexpr int sgm_warp_s
     return sgm_ns<PF, BULK>() * 32 * 2 * NR * 2 + (BULK ? ((sgm_ns<PF, BULK>() * 8 + 15) & ~15) : 0);
 }
 
+// base + 2 * idx as ONE IMAD.WIDE on the (idle) FMA pipe.  Left to itself the compiler builds the 64-bit address of a u16 element from a
+// 32-bit index with integer-ALU instructions (IADD3 / IADD3.X carry chains, or LEA + LEA.HI.X when it sees the constant 2) — on the pipe that
+// bounds the march.  `two` is the element size read from the kernel parameters, so that it stays a multiplication.
+__device__ __forceinline__ const uint16_t* sgm_elem(const uint16_t* base, const uint32_t idx, const uint32_t two) {
+    unsigned long long a;
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(a) : "r"(idx), "r"(two), "l"((unsigned long long)(uintptr_t)base));
+    return (const uint16_t*)(uintptr_t)a;
+}
+
 template <int NR, int PF, bool FULL, bool STORE, int BL, int BULK>
 struct SgmPipe {
     static constexpr int NS = sgm_ns<PF, BULK>(), NV = 2 * NR, STAGE = 32 * NV * 2;
@@ -136,7 +146,7 @@ struct SgmPipe {
     uint32_t ring;      // this lane's bytes inside stage 0
     uint32_t cell0;     // stage 0 (BULK)
     uint32_t bars;      // the stages' mbarriers (BULK)
-    uint32_t cell_bytes;
+    uint32_t cell_bytes, two;
     bool active, elect;
     __device__ __forceinline__ void init(const SgmParams& q, const uint32_t warp_base, const int lane, const bool active_) {
         constexpr int LANE_ELEMS = BL ? 4 : NV;
@@ -146,7 +156,7 @@ struct SgmPipe {
         C = BULK ? q.C : q.C + lane_c;
         S = BULK == 2 ? q.S : q.S + le;
         ring = warp_base + lane * (BL ? 8 : 4 * NR);
-        cell0 = warp_base; bars = warp_base + NS * STAGE; cell_bytes = 2u * D;
+        cell0 = warp_base; bars = warp_base + NS * STAGE; cell_bytes = 2u * D; two = q.elem_bytes;
         active = active_; elect = lane == 0;
         if (BULK) {
             if (elect) {
@@ -166,7 +176,7 @@ struct SgmPipe {
                 mbar_expect_tx(bars + 8 * slot, cell_bytes);
                 bulk_g2s(cell0 + slot * STAGE, C + ic, cell_bytes, bars + 8 * slot);
             }
-        } else if (active) V::cp_async(ring + slot * STAGE, C + ic);
+        } else if (active) V::cp_async(ring + slot * STAGE, sgm_elem(C, ic, two));
     }
     __device__ __forceinline__ void fill_end() const { if (!BULK) cp_async_commit(); }
     // the cell of step t (stage t % NS, used for the (t / NS)-th time) -> registers
@@ -178,7 +188,7 @@ struct SgmPipe {
     }
     // L of the cell just computed -> the cell at element index `is` of S; `slot` = the stage its C came from
     __device__ __forceinline__ void emit(const int slot, const uint32_t is, const uint32_t (&L)[NR]) const {
-        uint16_t* dst = S + is;
+        uint16_t* dst = BULK == 2 ? S + is : const_cast<uint16_t*>(sgm_elem(S, is, two));
         if (BULK == 2) {
             if (active) V::sts(ring + slot * STAGE, L);
             fence_proxy_async_smem();
@@ -757,6 +767,7 @@ static int fill_params(sva_ctx* ctx, SgmParams& q, const uint16_t* C, int c_ds) 
     q.C = C; q.S = ctx->S.as<uint16_t>(); q.W = p.width; q.H = p.height; q.D = p.num_disp; q.c_ds = c_ds;
     q.p1p1 = (uint32_t)p.p1 * 0x10001u; q.p2p2 = (uint32_t)p.p2 * 0x10001u;
     q.lanes = nr ? p.num_disp / (2 * nr) : 0;
+    q.elem_bytes = 2;
     return nr;
 }
 
