@@ -6,6 +6,8 @@ import numpy as np
 
 from stereovisionarray_b200 import abi, synth
 
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
 G = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
 
@@ -69,3 +71,16 @@ def test_depth_consumer_fixtures(oracle):
     assert np.array_equal(oracle.points3d_to_depth_map(cloud, cams[12], w // 2, h // 2), g["half_map"])
     groups = oracle.get_groups(25, "CHESS")
     assert [len(x) for x in groups] == list(g["group_sizes"]) and np.array_equal(np.concatenate(groups), g["group_pairs"])
+
+
+def test_c3_digest_inputs_are_what_the_generator_makes():
+    """tests/golden/c3_full_oracle.json holds digests of the ORACLE's maps of the full c3 frame (made by tests/golden/make_c3_hash.py; the
+    GPU tests re-derive them from a live oracle run).  Here, on CPU: the synthetic generator still produces the inputs those digests belong to."""
+    import hashlib
+    import json
+    from stereovisionarray_b200 import configs
+    with open(os.path.join(ROOT, "tests", "golden", "c3_full_oracle.json")) as f:
+        gold = json.load(f)
+    sc = configs.scene("c3")
+    assert hashlib.sha256(np.ascontiguousarray(np.stack([sc["ref"]] + list(sc["others"]))).tobytes()).hexdigest() == gold["inputs_sha256"]
+    assert gold["valid_pixels"] > 0.8 * 3840 * 2160 and len(gold["disp_sha256"]) == 64
