@@ -268,8 +268,12 @@ def run_sva(args):
             avg_ms = sum_ms / max(1, cnt)
             sym, what = split_label(kname)
             tr = traffic.get(kname)
+            # bytes the launch has to move: the schedule's count, or the measured DRAM traffic where the L2 serves part of that count (the
+            # horizontal SGM launch: -> and <- meet in the middle of a row) — so the fraction is of real HBM work and cannot exceed ~1
+            fb = min(sb, tr["dram_bytes"]) if (sb and tr) else sb
             rows.append({"kernel": sym, "launch": what or None, "launches_per_step": cnt / args.steps / frames_rank, "avg_ms": round(avg_ms, 4), "share": round(sum_ms / total_ms, 4),
-                         "schedule_bytes": sb, "achieved_gbs": round(sb / avg_ms / 1e6, 1) if sb else None, "frac": round(sb / avg_ms / 1e6 / peak, 4) if sb else None,
+                         "schedule_bytes": sb, "achieved_gbs": round(fb / avg_ms / 1e6, 1) if fb else None, "frac": round(fb / avg_ms / 1e6 / peak, 4) if fb else None,
+                         "frac_schedule": round(sb / avg_ms / 1e6 / peak, 4) if sb else None,
                          "frac_textbook": round(tb / avg_ms / 1e6 / peak, 4) if tb else None,
                          "traffic": int(tr["dram_bytes"]) if tr else None, "dram_frac": round(tr["dram_bytes"] / avg_ms / 1e6 / peak, 4) if tr else None,
                          "bound": tr["bound"] if tr else None, "ncu_pct": {k[:-4]: tr[k] for k in ("hbm_pct", "l1tex_pct", "alu_pct", "lsu_pct", "issue_pct", "warps_pct")} if tr else None})
@@ -285,7 +289,8 @@ def run_sva(args):
         roofline = {"bound": ("hbm" if dom["bound"] in (None, "hbm") else dom["bound"]) if dom["traffic"] else "hbm",
                     "bound_source": "ncu capture of this configuration (profiles/traffic.json)" if dom["traffic"] else "assumed: no ncu capture of this configuration and build in profiles/traffic.json",
                     "kernel": dom["kernel"], "launch": dom["launch"], "achieved": dom["achieved_gbs"], "peak": peak, "unit": "GB/s", "frac": dom["frac"],
-                    "frac_definition": "schedule bytes (DESIGN.md §4: what this launch must move given which directions share C and S in L2) / event-timed launch / measured HBM peak",
+                    "frac_definition": "min(schedule bytes, measured DRAM bytes of the ncu capture) / event-timed launch / measured HBM peak; schedule bytes = what this launch must move given which directions share C and S in L2 (DESIGN.md §6)",
+                    "frac_schedule": dom["frac_schedule"],
                     "frac_textbook": dom["frac_textbook"], "frac_of_8000": round(dom["achieved_gbs"] / 8000.0, 4),
                     "traffic": dom["traffic"], "dram_frac": dom["dram_frac"], "peak_source": peak_src,
                     "sgm_stage": dict(stage(sgm_sched, sgm_ms), textbook_bytes=int(sgm_text), frac_textbook=round(sgm_text / sgm_ms / 1e6 / peak, 4) if sgm_ms else None),
