@@ -183,7 +183,7 @@ int sva_ap_prepare(sva_ctx* ctx) {
     g.wp = g.txo * (g.strips - 1) + 256;
     const int need = kk + ((W + 7) & ~7);
     if (g.wp < need) g.wp = need;
-    g.wp = (g.wp + 3) & ~3;
+    g.wp = (g.wp + 7) & ~7;  // 32-byte rows: k_box_planar_shfl reads 32 bytes per lane
     g.hp = H + 2 * k;
     g.row_words = (size_t)(D >> 1) * g.wp;
     g.words = (size_t)g.hp * g.row_words;

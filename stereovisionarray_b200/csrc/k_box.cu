@@ -10,6 +10,8 @@
 // subtract the row leaving it).  The horizontal window sum is a difference of row prefix sums: every thread scans its
 // own NC columns in registers, segment totals are exchanged through shared memory, and the prefix row P lives in
 // shared memory for the two look-ups P[x+k-1] - P[x-k-1].  All sums are exact u32.
+#include <algorithm>
+
 #include "sva_common.cuh"
 
 #define BOX_THREADS 256
@@ -216,6 +218,8 @@ struct BoxPParams {
     int W, H, D, k, kk, dmin, shift, cap;
     int gxp, gxn, gyp, gyn;
     int band_rows, txo, wp;
+    int l2hint; // k_box_planar_shfl: 1 = entering rows evict_last, leaving rows and C evict_first
+    int chunk;  // k_box_planar_shfl: warm-up rows summed per horizontal pass (chunk x the largest A keeps a 16-bit field below 32768)
     long long row_words;
     int ry0, ry1;  // output rows [ry0, ry1) (the whole image, or a row block)
 };
@@ -380,6 +384,209 @@ k_box_planar(BoxPParams q) {
     store_row(y1 - y0 - 1);  // the last row's deferred store
 }
 
+// ---- K1b with the horizontal window sums in registers (win_half = K, K % 8 == 4: the configurations' K = 20, and 4, 12, 28, ...) ------
+// Same mapping as k_box_planar (warp = one disparity pair of a 256-column strip, lane = 8 consecutive columns), but the accumulators
+// are the WINDOW sums themselves, not column sums, and the per-warp prefix table in shared memory is gone.  Per row, u = enter - leave
+// + 0x80008000 is one word per column with two 16-bit fields (|enter - leave| <= 32 pairs x 255 keeps both fields positive), and what
+// the row adds to the window sum of column c is the sum of u over [c - K, c + K).  Because K % 8 == 4, the window of a lane's column 4
+// is exactly the lanes l - M .. l + M (M = (K - 4) / 8): lane totals, 2M shuffles.  From there the window slides one column at a time,
+//     dW(c + 1) = dW(c) + u(c + K) - u(c - K),
+// three steps up and four steps down, and the columns entering / leaving are whole packed words of other lanes: 14 shuffles per row
+// move BOTH cells of a word.  The two cells are carried as in k_box_planar: F = the whole-word sums (fields bleed, mod 2^32) and
+// Hh = the odd cell alone; (int)(u_a - u_b + 0x8000) >> 16 is the odd field's difference exactly, because the even field's
+// difference stays within +-32767.  Per row and 8 columns x 2 cells: 14 + 4M shuffles instead of 8 STS.64 + 16 LDS.64 + 10 shuffles.
+// Warm-up rows (the 2K - 1 rows before a band's first output) have nothing leaving, so they are summed as packed words first —
+// `chunk` rows at a time, as many as keep a field below 32768 — and only every chunk goes through the horizontal pass.
+template <int K, int PF, int OCC>
+__global__ void __launch_bounds__(256, OCC)
+k_box_planar_shfl(BoxPParams q) {
+    static_assert(K % 8 == 4 && K >= 4 && K <= 56, "window half-width must be 4 mod 8");
+    constexpr int M = (K - 4) / 8;
+    __shared__ __align__(16) uint32_t s_out[2][BXP_WARPS][BXP_OPITCH];
+    __shared__ __align__(8) unsigned long long s_bar[2];  // one mbarrier per staging buffer: "all 8 warps have written this row's words"
+    __shared__ int s_limy[BXP_MAX_BAND];
+    const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
+    const int W = q.W, H = q.H, D = q.D;
+    const int dpc = min((int)blockIdx.y * BXP_WARPS + warp, (D >> 1) - 1);  // warps beyond D/2 (D % 16 != 0) redo the last pair; never stored
+    const int d = 2 * dpc;
+    const int xs = blockIdx.x * q.txo - K;  // image x of strip column 0 (the left zero border is K columns: K % 4 == 0)
+    const int y0 = q.ry0 + blockIdx.z * q.band_rows, y1 = min(q.ry1, y0 + q.band_rows);
+    for (int i = t; i < y1 - y0; i += 256) s_limy[i] = axis_limit(y0 + i, H, K, q.gyp, q.gyn);
+
+    int thr[8], thrmin = 0x7FFFFFFF;  // validity slack of each column for this warp's even disparity
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        thr[j] = axis_limit(xs + lane * 8 + j, W, K, q.gxp, q.gxn) - q.dmin - d;
+        thrmin = min(thrmin, thr[j]);
+    }
+    const uint32_t bar0 = (uint32_t)__cvta_generic_to_shared(&s_bar[0]);
+    if (t == 0) {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0), "r"(BXP_WARPS) : "memory");
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar0 + 8), "r"(BXP_WARPS) : "memory");
+    }
+    __syncthreads();
+
+    // L2 policies: a row of A is read twice by this warp, 2K rows apart — entering (keep it: evict_last) and leaving (done: evict_first);
+    // C is written once and read by the next kernel only after the whole volume went by (evict_first)
+    const unsigned long long pol_enter = q.l2hint ? l2_policy_evict_last() : l2_policy_evict_normal();
+    const unsigned long long pol_leave = q.l2hint ? l2_policy_evict_first() : l2_policy_evict_normal();
+    const uint32_t* pe = q.AP + (size_t)dpc * q.wp + (size_t)blockIdx.x * q.txo + lane * 8 + (size_t)y0 * q.row_words;  // update n adds physical row y0 + n (image row y0 - K + n)
+    const long long back = 2LL * K * q.row_words;
+    const int N = (y1 - y0) + 2 * K - 1;
+    uint32_t F[8], Hh[8];
+#pragma unroll
+    for (int j = 0; j < 8; j++) { F[j] = 0; Hh[j] = 0; }
+
+    // per-thread output items: (column, half) pairs -> one 16-byte store each, pointers advance one image row per output row
+    const int hf = t & 1;
+    const bool half_ok = (int)blockIdx.y * 16 + 8 * hf < D;
+    const int xl0 = t >> 1, xl1 = xl0 + 128;
+    const bool st0 = half_ok && xl0 >= K && xl0 < K + q.txo && xs + xl0 < W;
+    const bool st1 = half_ok && xl1 >= K && xl1 < K + q.txo && xs + xl1 < W;
+    uint16_t* po = q.C + ((size_t)y0 * W + (xs + xl0)) * D + blockIdx.y * 16 + 8 * hf;  // item 1 is 128 columns further
+    const size_t orow = (size_t)W * D;
+
+    // transposed store of output row r (all 8 warps' words of that row are in s_out[r & 1] once the barrier's phase r >> 1 has completed)
+    auto store_row = [&](const int r) {
+        const uint32_t bar = bar0 + 8 * (r & 1), parity = (uint32_t)(r >> 1) & 1u;
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "BOXSWAIT_%=:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra BOXSDONE_%=;\n"
+            "bra BOXSWAIT_%=;\n"
+            "BOXSDONE_%=:\n"
+            "}" ::"r"(bar), "r"(parity) : "memory");
+        const uint32_t* src = &s_out[r & 1][4 * hf][xl0];
+        if (st0) stg_u128_hint(po, make_uint4(src[0], src[BXP_OPITCH], src[2 * BXP_OPITCH], src[3 * BXP_OPITCH]), pol_leave);
+        if (st1) stg_u128_hint(po + 128 * D, make_uint4(src[128], src[BXP_OPITCH + 128], src[2 * BXP_OPITCH + 128], src[3 * BXP_OPITCH + 128]), pol_leave);
+        po += orow;
+    };
+    // horizontal pass: the window sums of every column take in one row's (or one warm-up chunk's) packed differences u
+    auto hpass = [&](const uint32_t (&u)[8]) {
+        uint32_t tF = ((u[0] + u[1]) + (u[2] + u[3])) + ((u[4] + u[5]) + (u[6] + u[7]));
+        uint32_t tH = (((u[0] >> 16) + (u[1] >> 16)) + ((u[2] >> 16) + (u[3] >> 16))) + (((u[4] >> 16) + (u[5] >> 16)) + ((u[6] >> 16) + (u[7] >> 16)));
+        uint32_t dF[8], dH[8];
+        dF[4] = tF; dH[4] = tH;
+#pragma unroll
+        for (int s = 1; s <= M; s++) {
+            dF[4] += __shfl_up_sync(0xffffffffu, tF, s) + __shfl_down_sync(0xffffffffu, tF, s);
+            dH[4] += __shfl_up_sync(0xffffffffu, tH, s) + __shfl_down_sync(0xffffffffu, tH, s);
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {  // column 4 + i -> 5 + i: column 8(l + M + 1) + i enters, column 8(l - M) + i leaves
+            const uint32_t hi = __shfl_down_sync(0xffffffffu, u[i], M + 1);
+            const uint32_t lo = M == 0 ? u[i] : __shfl_up_sync(0xffffffffu, u[i], M == 0 ? 1 : M);
+            dF[5 + i] = dF[4 + i] + hi - lo;
+            dH[5 + i] = dH[4 + i] + (uint32_t)((int32_t)(hi - lo + 0x8000u) >> 16);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; i++) {  // column 4 - i -> 3 - i: column 8(l - M - 1) + 7 - i enters, column 8(l + M) + 7 - i leaves
+            const uint32_t hi = M == 0 ? u[7 - i] : __shfl_down_sync(0xffffffffu, u[7 - i], M == 0 ? 1 : M);
+            const uint32_t lo = __shfl_up_sync(0xffffffffu, u[7 - i], M + 1);
+            dF[3 - i] = dF[4 - i] - hi + lo;
+            dH[3 - i] = dH[4 - i] - (uint32_t)((int32_t)(hi - lo + 0x8000u) >> 16);
+        }
+        // every word of u carries the bias 0x80008000 (0x8000 on the odd field): 2K of them per window
+        constexpr uint32_t BF = (uint32_t)(2 * K) * 0x80008000u, BH = (uint32_t)(2 * K) * 0x8000u;
+#pragma unroll
+        for (int j = 0; j < 8; j++) { F[j] += dF[j] - BF; Hh[j] += dH[j] - BH; }
+    };
+    // output row `it`: shift / cap / validity of the lane's 8 words, staged for the transposed store
+    auto emit = [&](const int it) {
+        const int srow = s_limy[it] - q.dmin - d;
+        uint32_t w[8];
+        if (__all_sync(0xffffffffu, min(thrmin, srow) >= 1)) {  // every cell of the warp's 256 x 2 cells is valid (the image interior)
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t chi = Hh[j], clo = F[j] - (chi << 16);
+                const uint32_t c0 = min(clo >> q.shift, (uint32_t)q.cap), c1 = min(chi >> q.shift, (uint32_t)q.cap);
+                w[j] = c1 * 65536u + c0;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 8; j++) {
+                const uint32_t chi = Hh[j], clo = F[j] - (chi << 16);
+                uint32_t c0 = min(clo >> q.shift, (uint32_t)q.cap), c1 = min(chi >> q.shift, (uint32_t)q.cap);
+                const int m = min(thr[j], srow);
+                c0 = m >= 0 ? c0 : (uint32_t)q.cap;
+                c1 = m >= 1 ? c1 : (uint32_t)q.cap;
+                w[j] = c1 * 65536u + c0;
+            }
+        }
+        // split barrier as in k_box_planar: announce this row, store the previous one
+        if (it > 0) store_row(it - 1);
+        // a lane's 32 bytes go out as two 16-byte stores; lanes 4..7 of every eight store their upper half first, so that the eight lanes
+        // of a quarter-warp always hit eight different 16-byte bank groups (in lane order both halves would be 2-way conflicts)
+        uint32_t* so = &s_out[it & 1][warp][lane * 8];
+        const bool swz = (lane & 4) != 0;
+        *reinterpret_cast<uint4*>(so + (swz ? 4 : 0)) = swz ? make_uint4(w[4], w[5], w[6], w[7]) : make_uint4(w[0], w[1], w[2], w[3]);
+        *reinterpret_cast<uint4*>(so + (swz ? 0 : 4)) = swz ? make_uint4(w[0], w[1], w[2], w[3]) : make_uint4(w[4], w[5], w[6], w[7]);
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar0 + 8 * (it & 1)) : "memory");
+    };
+
+    // ---- warm-up: updates 0 .. 2K-2 (rows entering, nothing leaving, no output), packed sums of `chunk` rows per horizontal pass ----
+    {
+        uint32_t acc[8];
+#pragma unroll
+        for (int j = 0; j < 8; j++) acc[j] = 0x80008000u;
+        int cnt = 0;
+        U32x8 a = ldg_stream_u256(pe, pol_enter);
+        for (int n = 0; n < 2 * K - 1; n++) {
+            U32x8 b = a;
+            if (n + 1 < 2 * K - 1) { pe += q.row_words; b = ldg_stream_u256(pe, pol_enter); }
+#pragma unroll
+            for (int j = 0; j < 8; j++) acc[j] += a.v[j];
+            if (++cnt == q.chunk || n + 1 == 2 * K - 1) {
+                hpass(acc);
+#pragma unroll
+                for (int j = 0; j < 8; j++) acc[j] = 0x80008000u;
+                cnt = 0;
+            }
+            a = b;
+        }
+    }
+    // ---- steady state: update n = 2K-1+it adds physical row y0 + n, removes physical row y0 + n - 2K (zeros for it == 0), emits row it ----
+    {
+        const int R = y1 - y0;
+        auto fetch = [&](const int it, U32x8& e, U32x8& l) {
+            if (it < R) {
+                pe += q.row_words;
+                e = ldg_stream_u256(pe, pol_enter);
+                if (it > 0) l = ldg_stream_u256(pe - back, pol_leave);
+            }
+        };
+        auto row = [&](const int it, const U32x8& e, const U32x8& l) {
+            uint32_t u[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) u[j] = e.v[j] - l.v[j] + 0x80008000u;
+            hpass(u);
+            emit(it);
+        };
+        // software pipeline: the loads of row it + PF are issued before row it is worked on; PF + 1 register buffers rotate by unrolling
+        U32x8 be[PF + 1], bl[PF + 1];
+#pragma unroll
+        for (int i = 0; i <= PF; i++)
+#pragma unroll
+            for (int j = 0; j < 8; j++) { be[i].v[j] = 0; bl[i].v[j] = 0; }
+#pragma unroll
+        for (int i = 0; i < PF; i++) fetch(i, be[i], bl[i]);
+        for (int it = 0; it < R; it += PF + 1) {
+#pragma unroll
+            for (int i = 0; i <= PF; i++) {
+                if (it + i < R) {
+                    fetch(it + i + PF, be[(i + PF) % (PF + 1)], bl[(i + PF) % (PF + 1)]);
+                    row(it + i, be[i], bl[i]);
+                }
+            }
+        }
+        store_row(R - 1);  // the last row's deferred store
+    }
+    (void)N;
+}
+
 int sva_ap_prepare(sva_ctx* ctx);
 int sva_ap_unpack(sva_ctx* ctx);
 
@@ -398,27 +605,59 @@ static int sva_launch_box_planar(sva_ctx* ctx) {
     }
     q.txo = ctx->ap.txo; q.wp = ctx->ap.wp; q.row_words = (long long)ctx->ap.row_words;
     const int strips = ctx->ap.strips, dgroups = div_up(D, 16);
-    // Row bands: every band re-reads 2k-1 warm-up rows, and the grid should fill whole waves of the resident CTAs.  Pick the band
-    // count that minimises waves x rows marched per CTA.
-    int per_sm = 2;
-    SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_box_planar, 256, 0));
-    if (per_sm < 1) per_sm = 1;
-    const int slots = per_sm * ctx->sm_count, per_band = strips * dgroups;
-    int bands = 1;
-    double best = 1e30;
+    // the register form of the horizontal sums needs win_half % 8 == 4 (k_box_planar_shfl); everything else takes the prefix table
+    const bool shfl = ctx->tune_box_shfl && k % 8 == 4;
+    auto shfl_kernel = [&](int occ) -> void (*)(BoxPParams) {
+        switch (k) {
+            case 4: return occ == 3 ? k_box_planar_shfl<4, 1, 3> : k_box_planar_shfl<4, 1, 2>;
+            case 12: return occ == 3 ? k_box_planar_shfl<12, 1, 3> : k_box_planar_shfl<12, 1, 2>;
+            case 20: return occ == 3 ? k_box_planar_shfl<20, 1, 3> : k_box_planar_shfl<20, 1, 2>;
+            case 28: return occ == 3 ? k_box_planar_shfl<28, 1, 3> : k_box_planar_shfl<28, 1, 2>;
+            case 36: return occ == 3 ? k_box_planar_shfl<36, 1, 3> : k_box_planar_shfl<36, 1, 2>;
+            case 44: return occ == 3 ? k_box_planar_shfl<44, 1, 3> : k_box_planar_shfl<44, 1, 2>;
+            default: return occ == 3 ? k_box_planar_shfl<52, 1, 3> : k_box_planar_shfl<52, 1, 2>;
+        }
+    };
+    if (shfl) {
+        q.chunk = std::max(1, 32767 / (255 * p.n_pairs));
+        q.l2hint = ctx->tune_box_l2 ? 1 : 0;
+    }
     q.ry0 = 0; q.ry1 = H;
     if (ctx->win_rows > 0) { q.ry0 = ctx->win_y0; q.ry1 = ctx->win_y0 + ctx->win_rows; }
     const int Hw = q.ry1 - q.ry0;
-    for (int b = 1; b <= Hw && b <= 4096; b++) {
-        const int rows = div_up(Hw, b);
-        if (rows > BXP_MAX_BAND) continue;
-        if (b > 1 && rows < k) break;
-        const int nb = div_up(Hw, rows);
-        const double cost = (double)div_up(nb * per_band, slots) * (rows + 2 * k - 1 + 8);
-        if (cost < best) { best = cost; bands = nb; q.band_rows = rows; }
+    // Row bands and CTAs per SM.  Every band re-reads 2k-1 warm-up rows (in the register form a third of an output row's DRAM traffic each,
+    // and one horizontal pass per chunk), and the grid should fill whole waves of the resident CTAs.  The register form exists for 2 CTAs
+    // per SM (up to 128 registers) and for 3 (80 registers, no spills): per row a CTA costs about the same either way and the SM's
+    // throughput is shared, so the estimate is waves x CTAs per SM x rows marched per CTA — 3 per SM wins where 2 per SM would leave a
+    // wave partly empty (c2, c4: 0.335 -> 0.309 ms, 0.617 -> 0.571 ms), 2 per SM where the bands are long anyway (c1, c3).
+    void (*kern)(BoxPParams) = k_box_planar;
+    const char* label = shfl ? "k_box_planar_shfl" : "k_box_planar";
+    int bands = 1;
+    double best = 1e30;
+    const int per_band = strips * dgroups;
+    for (int occ = 2; occ <= (shfl ? 3 : 2); occ++) {
+        if (shfl && ctx->tune_box_occ && occ != ctx->tune_box_occ) continue;
+        void (*cand)(BoxPParams) = shfl ? shfl_kernel(occ) : k_box_planar;
+        int per_sm = occ;
+        SVA_CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, cand, 256, 0));
+        if (per_sm < 1) per_sm = 1;
+        const int slots = per_sm * ctx->sm_count;
+        const double warm = shfl ? (2 * k - 1) / 3.0 + div_up(2 * k - 1, q.chunk) : (double)(2 * k - 1);
+        for (int b = 1; b <= Hw && b <= 4096; b++) {
+            const int rows = div_up(Hw, b);
+            if (rows > BXP_MAX_BAND) continue;
+            if (b > 1 && rows < k) break;
+            const int nb = div_up(Hw, rows);
+            const double cost = (double)div_up(nb * per_band, slots) * per_sm * (rows + warm + 8);
+            if (cost < best) { best = cost; bands = nb; q.band_rows = rows; kern = cand; }
+        }
     }
-    LaunchScope ls(ctx, "k_box_planar");
-    k_box_planar<<<dim3(strips, dgroups, bands), 256, 0, ctx->stream>>>(q);
+    if (ctx->tune_box_bands > 0) {
+        const int rows = std::min(BXP_MAX_BAND, std::max(1, div_up(Hw, ctx->tune_box_bands)));
+        q.band_rows = rows; bands = div_up(Hw, rows);
+    }
+    LaunchScope ls(ctx, label);
+    kern<<<dim3(strips, dgroups, bands), 256, 0, ctx->stream>>>(q);
     SVA_CUDA_OK(ctx, cudaGetLastError());
     return SVA_OK;
 }

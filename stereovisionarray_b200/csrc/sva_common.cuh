@@ -102,6 +102,12 @@ struct sva_ctx {
                                   // 0 (default, fastest measured) = per-lane cp.async / RED
     int tune_sgm_diag_split = 1;  // SVA_SGM_DIAG_SPLIT: diagonal lines run the march that is split at the wrap events (no per-step wrap logic)
     int tune_ad_gather = 0;       // SVA_AD_GATHER=1: force the line-image gather AD kernel (k_ad.cu) even where the image-space kernel applies
+    int tune_ad_set = 1;          // SVA_AD_SET: use the AD kernel compiled for the frame's pair set where one exists (0 = always the generic kernel)
+    int tune_ad_th = 0;           // SVA_AD_TH: rows per tile of the image-space AD kernel (0 = chosen per launch, k_ad2.cu)
+    int tune_box_l2 = 0;          // SVA_BOX_L2: K1b's entering rows stay in L2 (evict_last) for their second read as leaving rows (evict_first, like the C stores)
+    int tune_box_occ = 0;         // SVA_BOX_OCC: CTAs per SM K1b is compiled for (2: up to 128 registers, 3: 80; 0 = chosen per launch)
+    int tune_box_bands = 0;       // SVA_BOX_BANDS: row bands of K1b (0 = chosen per launch)
+    int tune_box_shfl = 1;        // SVA_BOX_SHFL: K1b's horizontal window sums by warp shuffles where win_half % 8 == 4 (0 = the shared-memory prefix table)
     int tune_wta_seg = 160;       // SVA_WTA_SEG: K3 as a register march over row segments of this many pixels (0 = the shared-memory tile kernel)
     uint32_t sgm_dir_mask_override = 0;  // tests: run exactly these directions as accumulate passes (no final pass)
     PairGeom geom[SVA_MAX_PAIRS];
@@ -172,5 +178,33 @@ __device__ __forceinline__ uint4 ldg_stream_u128(const void* p) {
     uint4 v;
     asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
+}
+// 32 bytes per lane in ONE instruction (LDG.E.256, sm_100): a warp-load covers 1 KB of whole sectors.  `policy` is an L2 eviction
+// policy word from l2_policy_* below.  The address must be 32-byte aligned.
+struct U32x8 { uint32_t v[8]; };
+__device__ __forceinline__ U32x8 ldg_stream_u256(const void* p, const unsigned long long policy) {
+    U32x8 r;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v8.u32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8], %9;"
+                 : "=r"(r.v[0]), "=r"(r.v[1]), "=r"(r.v[2]), "=r"(r.v[3]), "=r"(r.v[4]), "=r"(r.v[5]), "=r"(r.v[6]), "=r"(r.v[7])
+                 : "l"(p), "l"(policy));
+    return r;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_last() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_first() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ unsigned long long l2_policy_evict_normal() {
+    unsigned long long pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ void stg_u128_hint(void* p, const uint4& v, const unsigned long long policy) {
+    asm volatile("st.global.L2::cache_hint.v4.u32 [%0], {%1, %2, %3, %4}, %5;" ::"l"(p), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w), "l"(policy) : "memory");
 }
 #endif

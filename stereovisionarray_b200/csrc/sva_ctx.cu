@@ -102,6 +102,12 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_DIAG_SPLIT")) c->tune_sgm_diag_split = atoi(e);
     if (const char* e = getenv("SVA_WTA_SEG")) c->tune_wta_seg = atoi(e);
     if (const char* e = getenv("SVA_AD_GATHER")) c->tune_ad_gather = atoi(e);
+    if (const char* e = getenv("SVA_AD_TH")) c->tune_ad_th = atoi(e);
+    if (const char* e = getenv("SVA_BOX_SHFL")) c->tune_box_shfl = atoi(e);
+    if (const char* e = getenv("SVA_BOX_L2")) c->tune_box_l2 = atoi(e);
+    if (const char* e = getenv("SVA_BOX_BANDS")) c->tune_box_bands = atoi(e);
+    if (const char* e = getenv("SVA_BOX_OCC")) c->tune_box_occ = atoi(e);
+    if (const char* e = getenv("SVA_AD_SET")) c->tune_ad_set = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE_WINDOW")) c->tune_sgm_pace_window = atoi(e);
     *out = c;
     return SVA_OK;

@@ -12,6 +12,7 @@ ap.add_argument("--config", default="c1")
 ap.add_argument("--win-half", type=int, default=20)
 ap.add_argument("--iters", type=int, default=2)
 ap.add_argument("--times", action="store_true", help="print the CUDA-event time of every launch of one more frame")
+ap.add_argument("--avg", type=int, default=0, help="print the average CUDA-event time per kernel over this many more frames")
 ap.add_argument("--size", default="", help="WxHxD: a 3x3-array frame of random pixels of this size instead of a named config")
 a = ap.parse_args()
 if a.size:
@@ -32,4 +33,7 @@ ctx.synchronize()
 if a.times:
     kt = ctx.kernel_times(abi.STAGE_ALL)
     print(" ".join("%s=%.4f" % (n, ms) for n, ms in kt), "total=%.4f" % sum(ms for _, ms in kt))
+if a.avg:
+    tot, per = ctx.time_detailed(abi.STAGE_ALL, a.avg)
+    print(" ".join("%s=%.4f" % (n.split("/")[0][:24], sm / a.avg) for n, (sm, c) in per.items()), "total=%.4f" % (tot / a.avg))
 print("ok", ctx.launches())
