@@ -86,9 +86,9 @@ def schedule_bytes(label, p, n_cam):
     de = p.width * p.height * p.num_disp
     px = p.width * p.height
     sym, what = split_label(label)
-    if sym in ("k_ad_planar", "k_ad_tile"):
+    if sym in ("k_ad_planar", "k_ad_tile") or sym.startswith("k_ad_tile"):
         return n_cam * px + 2 * de          # views in, A out
-    if sym in ("k_box_cost", "k_box_planar"):
+    if sym in ("k_box_cost", "k_box_planar") or sym.startswith("k_box_planar"):
         return 4 * de                       # A in, C out
     if sym.startswith("k_sgm_acc"):
         n = int(what[-1]) if what and what[-1].isdigit() else 1

@@ -31,8 +31,9 @@
 #define AD2_MAXG 2
 #define AD2_SMEM_BUDGET (110 * 1024)   // two CTAs per SM
 
-__host__ __device__ constexpr int ad2_sp(int agx) { return agx == 0 ? 160 : (agx == 1 ? 192 : 224); }  // staged row pitch, bytes
-__host__ __device__ constexpr int ad2_rows(int agy, int th) { return th + (AD2_DR - 1) * agy; }
+// staged row pitch, bytes: 128 columns + (dr - 1) * |gx| + up to 15 bytes of alignment + 3 of the last unaligned word, in whole 16-byte chunks
+__host__ __device__ constexpr int ad2_sp(int agx, int dr = AD2_DR) { return dr == 32 ? (agx == 0 ? 160 : (agx == 1 ? 192 : 224)) : (agx == 0 ? 160 : (agx == 1 ? 176 : 192)); }
+__host__ __device__ constexpr int ad2_rows(int agy, int th, int dr = AD2_DR) { return th + (dr - 1) * agy; }
 #define AD2_TH_MAX 48
 
 struct Ad2Params {
@@ -56,9 +57,9 @@ struct Ad2Params {
 
 // accumulate one pair into the thread's 16 disparities x 4 pixels; bp = word-aligned shared pointer of (this row, this quad, disparity 0)
 // ax[i] += the word of four byte differences (fields bleed), ao[i] += pixels 1 and 3 as u16x2; see the header
-template <int GX, int GY, bool FMA = false>
+template <int GX, int GY, bool FMA = false, int DR = AD2_DR>
 __device__ __forceinline__ void ad2_pair(const uint32_t* __restrict__ bp, const uint32_t r, uint32_t (&ax)[16], uint32_t (&ao)[16], const uint32_t one = 1u) {
-    constexpr int SP = ad2_sp(GX < 0 ? -GX : GX);
+    constexpr int SP = ad2_sp(GX < 0 ? -GX : GX, DR);
 #pragma unroll
     for (int i = 0; i < 16; i++) {
         const int boff = -i * (GY * SP + GX);            // byte offset of disparity i's source word
@@ -127,19 +128,20 @@ struct Ad2Shared {
 
 // stage pairs [kb, ke): one thread per pair works out the pair's rectangle, then every thread copies 16-byte chunks t, t + 512, ... of
 // each rectangle (chunk c = row c / cpr, column chunk c % cpr); returns with the copies complete and visible to the CTA
+template <int DR = AD2_DR>
 __device__ __forceinline__ void ad2_stage(const Ad2Params& q, Ad2Shared& sh, unsigned char* smem, const int kb, const int ke, const int x0, const int y0, const int da) {
     const int t = threadIdx.x, th = q.th;
     if (t < ke - kb) {
         const int k = kb + t;
         const int gx = q.gx[k], gy = q.gy[k];
         int soff = 0;
-        for (int j = kb; j < k; j++) soff += ad2_rows(q.gy[j] < 0 ? -q.gy[j] : q.gy[j], th) * ad2_sp(q.gx[j] < 0 ? -q.gx[j] : q.gx[j]);
-        const int sp = ad2_sp(gx < 0 ? -gx : gx), rows = ad2_rows(gy < 0 ? -gy : gy, th);
+        for (int j = kb; j < k; j++) soff += ad2_rows(q.gy[j] < 0 ? -q.gy[j] : q.gy[j], th, DR) * ad2_sp(q.gx[j] < 0 ? -q.gx[j] : q.gx[j], DR);
+        const int sp = ad2_sp(gx < 0 ? -gx : gx, DR), rows = ad2_rows(gy < 0 ? -gy : gy, th, DR);
         // first staged row / column in view coordinates (disparity index AD2_DR-1 reaches furthest towards -g)
-        const int ylo = y0 - gy * (q.dmin + da) - (gy > 0 ? (AD2_DR - 1) * gy : 0);
-        const int v = q.padx + q.phi[k] + x0 - gx * (q.dmin + da) - (gx > 0 ? (AD2_DR - 1) * gx : 0);
+        const int ylo = y0 - gy * (q.dmin + da) - (gy > 0 ? (DR - 1) * gy : 0);
+        const int v = q.padx + q.phi[k] + x0 - gx * (q.dmin + da) - (gx > 0 ? (DR - 1) * gx : 0);
         const int c0 = v & ~15, e = v - c0;
-        sh.pk[k] = make_int4(soff + (gx > 0 ? (AD2_DR - 1) * gx : 0) + e + (gy > 0 ? (AD2_DR - 1) * gy : 0) * sp, sp, 16 * (gy * sp + gx), (gx + 2) * 5 + gy + 2);
+        sh.pk[k] = make_int4(soff + (gx > 0 ? (DR - 1) * gx : 0) + e + (gy > 0 ? (DR - 1) * gy : 0) * sp, sp, 16 * (gy * sp + gx), (gx + 2) * 5 + gy + 2);
         sh.src[k] = q.imgs + (size_t)q.img[k] * q.img_bytes + (size_t)(q.pady + ylo) * q.pp + c0;
         sh.geo[k] = make_int2(soff, rows);
     }
@@ -234,55 +236,73 @@ k_ad_tile(const Ad2Params q) {
 }
 
 // ---- the same kernel with the pair set known at compile time ----------------------------------------------------------------------
-// CODE packs the body index (gx + 2) * 5 + gy + 2 of pair k into bits [5k, 5k + 5), NP pairs, one staging group.  With the set fixed the
-// pair loop is straight-line code: no dispatch, no common accumulate block that the 25 bodies of the generic kernel jump to (and that
-// forces all 32 of a body's results to be live at once), and the scheduler can overlap one pair's shared-memory loads with the previous
-// pair's arithmetic.  Instantiated for the grids of the configurations (sva_run_ad2); every other pair set runs k_ad_tile.
-template <unsigned long long CODE, int K, int NP>
+// SET::n pairs with grid offsets SET::gx[k], SET::gy[k], one staging group.  With the set fixed the pair loop is straight-line code: no
+// dispatch, no common accumulate block that the 25 bodies of the generic kernel jump to (and that forces all 32 of a body's results to be
+// live at once), and the scheduler can overlap one pair's shared-memory loads with the previous pair's arithmetic; the accumulation is
+// written as IMADs (Ad2Params::one).  DR = disparities per CTA: 32 (a thread = 4 pixels x 16 disparities, two threads per quad and row,
+// 8 rows per pass) or 16 (one thread per quad and row, 16 rows per pass) — the 15 pairs of a 4 x 4 array reach two baselines, and only
+// with 16 disparities per CTA do their staged rows (th + 15 * |gy| instead of th + 31 * |gy|) fit one group at th = 16.
+// Instantiated for the grids of the configurations (sva_run_ad2); every other pair set runs k_ad_tile.
+struct Ad2Set3x3 {  // 3 x 3 array, reference in the centre, views in index order (c1, c2, c4)
+    static constexpr int n = 8, dr = 32;
+    static constexpr int gx[8] = {-1, 0, 1, -1, 1, -1, 0, 1};
+    static constexpr int gy[8] = {-1, -1, -1, 0, 0, 1, 1, 1};
+};
+struct Ad2SetPair {  // rectified pair, the other camera one baseline to the left (c0)
+    static constexpr int n = 1, dr = 32;
+    static constexpr int gx[1] = {-1};
+    static constexpr int gy[1] = {0};
+};
+struct Ad2Set4x4 {  // 4 x 4 array, reference at (1, 1), views in index order (c3)
+    static constexpr int n = 15, dr = 16;
+    static constexpr int gx[15] = {-1, 0, 1, 2, -1, 1, 2, -1, 0, 1, 2, -1, 0, 1, 2};
+    static constexpr int gy[15] = {-1, -1, -1, -1, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2};
+};
+
+template <class SET, int K>
 struct Ad2Seq {
     static __device__ __forceinline__ void run(const Ad2Shared& sh, const unsigned char* smem, const int yt, const int sub, const int quad, const uint32_t r,
                                                uint32_t (&ax)[16], uint32_t (&ao)[16], const uint32_t one) {
-        constexpr int type = (int)((CODE >> (5 * K)) & 31ull);
-        const int4 pk = sh.pk[K];
-        const uint32_t* bp = reinterpret_cast<const uint32_t*>(smem + (pk.x + yt * pk.y - sub * pk.z + 4 * quad));
-        ad2_pair<type / 5 - 2, type % 5 - 2, true>(bp, r, ax, ao, one);
-        Ad2Seq<CODE, K + 1, NP>::run(sh, smem, yt, sub, quad, r, ax, ao, one);
+        if constexpr (K < SET::n) {
+            const int4 pk = sh.pk[K];
+            const uint32_t* bp = reinterpret_cast<const uint32_t*>(smem + (pk.x + yt * pk.y - sub * pk.z + 4 * quad));
+            ad2_pair<SET::gx[K], SET::gy[K], true, SET::dr>(bp, r, ax, ao, one);
+            Ad2Seq<SET, K + 1>::run(sh, smem, yt, sub, quad, r, ax, ao, one);
+        }
     }
 };
-template <unsigned long long CODE, int NP>
-struct Ad2Seq<CODE, NP, NP> {
-    static __device__ __forceinline__ void run(const Ad2Shared&, const unsigned char*, int, int, int, uint32_t, uint32_t (&)[16], uint32_t (&)[16], uint32_t) {}
-};
 
-template <unsigned long long CODE, int NP>
+template <class SET>
 __global__ void __launch_bounds__(AD2_THREADS, 2)
 k_ad_tile_set(const Ad2Params q) {
+    constexpr int DR = SET::dr, SUBS = DR / 16, RSTEP = AD2_THREADS / (32 * SUBS);  // rows per pass: 8 (DR = 32) or 16 (DR = 16)
     extern __shared__ __align__(16) unsigned char ad2_smem[];
     __shared__ Ad2Shared sh;
     const int t = threadIdx.x;
-    const int quad = t & 31, sub = (t >> 5) & 1, yl = t >> 6;
-    const int x0 = blockIdx.x * AD2_TW, y0 = q.row0 + blockIdx.y * q.th, da = blockIdx.z * AD2_DR;
+    const int quad = t & 31, sub = (t >> 5) % SUBS, yl = t / (32 * SUBS);
+    const int x0 = blockIdx.x * AD2_TW, y0 = q.row0 + blockIdx.y * q.th, da = blockIdx.z * DR;
     const int x = x0 + 4 * quad, d0 = da + 16 * sub;
-    ad2_stage(q, sh, ad2_smem, 0, NP, x0, y0, da);
-    const int rows = min(q.th, q.row1 - y0);  // rows of this tile inside the launch's range, walked in whole groups of 8
+    ad2_stage<DR>(q, sh, ad2_smem, 0, SET::n, x0, y0, da);
+    const int rows = min(q.th, q.row1 - y0);  // rows of this tile inside the launch's range, walked in whole passes
 #pragma unroll 1
-    for (int yt = yl; yt - yl < rows; yt += AD2_TH) {
+    for (int yt = yl; yt - yl < rows; yt += RSTEP) {
         const int y = y0 + yt;
         const uint32_t r = *reinterpret_cast<const uint32_t*>(q.ref + (size_t)y * q.rp + x);
         uint32_t ax[16], ao[16];
 #pragma unroll
         for (int i = 0; i < 16; i++) { ax[i] = 0; ao[i] = 0; }
-        Ad2Seq<CODE, 0, NP>::run(sh, ad2_smem, yt, sub, quad, r, ax, ao, q.one);
+        Ad2Seq<SET, 0>::run(sh, ad2_smem, yt, sub, quad, r, ax, ao, q.one);
         ad2_store(q, y, x, d0, ax, ao);
     }
 }
 
-constexpr unsigned long long ad2_type(int gx, int gy) { return (unsigned long long)((gx + 2) * 5 + gy + 2); }
-// 3 x 3 array, reference in the centre, views in index order (c1, c2, c4)
-constexpr unsigned long long AD2_SET_3X3 = ad2_type(-1, -1) | ad2_type(0, -1) << 5 | ad2_type(1, -1) << 10 | ad2_type(-1, 0) << 15 | ad2_type(1, 0) << 20 |
-                                           ad2_type(-1, 1) << 25 | ad2_type(0, 1) << 30 | ad2_type(1, 1) << 35;
-// rectified pair, the other camera one baseline to the left (c0)
-constexpr unsigned long long AD2_SET_PAIR = ad2_type(-1, 0);
+template <class SET>
+static bool ad2_set_matches(const Ad2Params& q) {
+    if (q.n != SET::n) return false;
+    for (int i = 0; i < SET::n; i++)
+        if (q.gx[i] != SET::gx[i] || q.gy[i] != SET::gy[i]) return false;
+    return true;
+}
 
 // ---- host side ------------------------------------------------------------------------------------------------------------------
 bool sva_ad2_usable(const sva_params& p) {
@@ -359,22 +379,32 @@ int sva_run_ad2(sva_ctx* ctx) {
     int ya = 0, yb = H;
     if (ctx->win_rows > 0) { ya = std::max(0, ctx->win_y0 - p.win_half); yb = std::min(H, ctx->win_y0 + ctx->win_rows + p.win_half); }
     q.row0 = ya / AD2_TH * AD2_TH; q.row1 = yb;
-    // Tile height: a tile stages th + 31 * |gy| rows of every view, so tall tiles cost less staging and set-up per row — but the grid
-    // should fill whole waves of the 2 CTAs per SM.  Among the heights whose pairs fit one staging group, take the one that minimises
-    // waves x (rows per tile + set-up, in row equivalents); if even 8 rows need several groups (c3: 15 pairs), th = 8.
+    // The kernel: one compiled for the frame's pair set where there is one (it also fixes the disparities per CTA), else the generic one.
+    void (*kern)(Ad2Params) = nullptr;
+    int dr = AD2_DR;
+    if (ctx->tune_ad_set) {
+        if (ad2_set_matches<Ad2Set3x3>(q)) { kern = k_ad_tile_set<Ad2Set3x3>; dr = Ad2Set3x3::dr; }
+        else if (ad2_set_matches<Ad2SetPair>(q)) { kern = k_ad_tile_set<Ad2SetPair>; dr = Ad2SetPair::dr; }
+        else if (ad2_set_matches<Ad2Set4x4>(q)) { kern = k_ad_tile_set<Ad2Set4x4>; dr = Ad2Set4x4::dr; }
+    }
+    const int rstep = dr == 32 ? 8 : 16;  // rows per pass of the CTA's 512 threads
+    // Tile height: a tile stages th + (dr - 1) * |gy| rows of every view, so tall tiles cost less staging and set-up per row — but the grid
+    // should keep several waves of the 2 CTAs per SM.  Measured (B200, c1 / c4): 24 - 32 rows are best as long as the grid still has five
+    // or more waves; small frames keep one pass per tile.  A pair set without a compiled kernel whose 8-row tile does not fit one staging
+    // group runs the generic kernel with several groups.
     auto bytes_for = [&](int th) {
         size_t b = 0;
-        for (int i = 0; i < q.n; i++) b += (size_t)ad2_rows(abs(q.gy[i]), th) * ad2_sp(abs(q.gx[i]));
+        for (int i = 0; i < q.n; i++) b += (size_t)ad2_rows(abs(q.gy[i]), th, dr) * ad2_sp(abs(q.gx[i]), dr);
         return b;
     };
-    const int tiles_x = div_up(W, AD2_TW), tiles_d = div_up(D, AD2_DR), slots = 2 * ctx->sm_count;
-    int th = AD2_TH;
+    const int tiles_x = div_up(W, AD2_TW), tiles_d = div_up(D, dr), slots = 2 * ctx->sm_count;
+    if (kern && bytes_for(rstep) > AD2_SMEM_BUDGET) { kern = nullptr; dr = AD2_DR; }
+    int th = kern ? rstep : AD2_TH;
     if (ctx->tune_ad_th > 0) {
-        th = std::min(AD2_TH_MAX, ctx->tune_ad_th / AD2_TH * AD2_TH);
-        if (th < AD2_TH || bytes_for(th) > AD2_SMEM_BUDGET) th = AD2_TH;
+        const int want = std::min(AD2_TH_MAX, ctx->tune_ad_th / th * th);
+        if (want >= th && bytes_for(want) <= AD2_SMEM_BUDGET) th = want;
     } else {
-        // measured (B200, c1 / c4): 24 - 32 rows are best as long as the grid still has five or more waves; small frames keep 8 rows
-        for (int cand = 32; cand > AD2_TH; cand -= AD2_TH) {
+        for (int cand = 32; cand > th; cand -= (kern ? rstep : AD2_TH)) {
             if (bytes_for(cand) > AD2_SMEM_BUDGET) continue;
             if (tiles_x * tiles_d * div_up(q.row1 - q.row0, cand) >= 5 * slots) { th = cand; break; }
         }
@@ -383,22 +413,15 @@ int sva_run_ad2(sva_ctx* ctx) {
     size_t group_bytes = 0, max_group = 0;
     q.ngroups = 0; q.gbeg[0] = 0;
     for (int i = 0; i < q.n; i++) {
-        const size_t bytes = (size_t)ad2_rows(abs(q.gy[i]), th) * ad2_sp(abs(q.gx[i]));
+        const size_t bytes = (size_t)ad2_rows(abs(q.gy[i]), th, dr) * ad2_sp(abs(q.gx[i]), dr);
         if (group_bytes + bytes > AD2_SMEM_BUDGET && group_bytes > 0) { q.gbeg[++q.ngroups] = (uint8_t)i; group_bytes = 0; }
         group_bytes += bytes;
         max_group = std::max(max_group, group_bytes);
     }
     q.gbeg[++q.ngroups] = (uint8_t)q.n;
     const size_t smem = max_group + 16;
-    const bool multi = q.ngroups > 1;
-    unsigned long long code = 0;
-    for (int i = 0; i < q.n && i < 12; i++) code |= ad2_type(q.gx[i], q.gy[i]) << (5 * i);
-    void (*kern)(Ad2Params) = multi ? k_ad_tile<true> : k_ad_tile<false>;
-    const char* label = "k_ad_tile";
-    if (!multi && ctx->tune_ad_set) {
-        if (q.n == 8 && code == AD2_SET_3X3) { kern = k_ad_tile_set<AD2_SET_3X3, 8>; label = "k_ad_tile_set"; }
-        else if (q.n == 1 && code == AD2_SET_PAIR) { kern = k_ad_tile_set<AD2_SET_PAIR, 1>; label = "k_ad_tile_set"; }
-    }
+    const char* label = kern ? "k_ad_tile_set" : "k_ad_tile";
+    if (!kern) kern = q.ngroups > 1 ? k_ad_tile<true> : k_ad_tile<false>;
     SVA_CUDA_OK(ctx, cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     {
         LaunchScope ls(ctx, label);
