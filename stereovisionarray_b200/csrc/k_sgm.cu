@@ -843,6 +843,61 @@ int sva_run_sgm(sva_ctx* ctx) {
         ctx->have_sgm = false; ctx->have_disp = true;
         return SVA_OK;
     }
+    // wall time of the aggregation stage (its launches may overlap: entry "stage:k2_sgm" of the timing table, not a kernel)
+    struct StageWall {
+        sva_ctx* c; cudaEvent_t beg = nullptr, end = nullptr;
+        explicit StageWall(sva_ctx* ctx) : c(ctx) {
+            if (!c->timing) return;
+            while (c->event_pool.size() < c->events_used + 2) { cudaEvent_t e; cudaEventCreate(&e); c->event_pool.push_back(e); }
+            beg = c->event_pool[c->events_used]; end = c->event_pool[c->events_used + 1];
+            c->events_used += 2;
+            cudaEventRecord(beg, c->stream);
+        }
+        void stop() {
+            if (!beg) return;
+            cudaEventRecord(end, c->stream);
+            c->ktimes.push_back(KernelTime{"stage:k2_sgm", beg, end});
+            beg = nullptr;
+        }
+    } wall(ctx);
+    if (n == 8 && ctx->tune_sgm_split && ctx->tune_sgm_hstore && !ctx->s_prezeroed) {
+        // S is never zeroed: the first horizontal direction WRITES it (plain stores: C in, S out = 4 B/DE), the second accumulates (6 B/DE), then
+        // the row-sweeping groups — 10 B/DE for the horizontal pair instead of 12 plus the 2 B/DE of the memset that ran next to K1
+        static const int grp[3][3] = {{0, 4, 5}, {1, 6, 7}, {2, 3, -1}};
+        const int h0 = 2, h1 = 3;
+        set_dirs(q, &h0, 1);
+        SVA_TRY(launch_dirs(ctx, q, nr, true));
+        // The second horizontal direction is a launch of H warps bound by the latency of its own recurrence (~200 clocks per step): with
+        // SVA_SGM_HSTORE = 2 it runs on the second stream NEXT TO the first row-sweeping group (REDs commute; both start after the stores).
+        const bool side = ctx->tune_sgm_hstore == 3 || (ctx->tune_sgm_hstore == 2 && q.W * (size_t)q.D * 4 < 768 * 1024);  // not next to paced launches: they want the SM to themselves
+        cudaStream_t main_stream = ctx->stream;
+        if (side) {
+            if (!ctx->aux_stream) {
+                SVA_CUDA_OK(ctx, cudaStreamCreateWithFlags(&ctx->aux_stream, cudaStreamNonBlocking));
+                SVA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+            }
+            if (!ctx->ev_zero) SVA_CUDA_OK(ctx, cudaEventCreateWithFlags(&ctx->ev_zero, cudaEventDisableTiming));
+            SVA_CUDA_OK(ctx, cudaEventRecord(ctx->ev_fork, main_stream));
+            SVA_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->aux_stream, ctx->ev_fork, 0));
+            ctx->stream = ctx->aux_stream;
+        }
+        set_dirs(q, &h1, 1);
+        const int rc_h1 = launch_dirs(ctx, q, nr, false);
+        if (side) {
+            ctx->stream = main_stream;
+            if (rc_h1 == SVA_OK) SVA_CUDA_OK(ctx, cudaEventRecord(ctx->ev_zero, ctx->aux_stream));
+        }
+        SVA_TRY(rc_h1);
+        for (int g = 0; g < 2; g++) {
+            if (group_needs_blocks(ctx, q, nr, 3)) SVA_TRY(run_group_in_blocks(ctx, q, nr, grp[g], 3));
+            else SVA_TRY(launch_row_group(ctx, q, nr, grp[g], 3));
+        }
+        if (side) SVA_CUDA_OK(ctx, cudaStreamWaitEvent(main_stream, ctx->ev_zero, 0));
+        wall.stop();
+        SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
+        ctx->have_sgm = true; ctx->have_disp = true;
+        return SVA_OK;
+    }
     // S = 0 (zeroed next to K1a / K1b when the caller got that far ahead: sva_api.cu), every path accumulates with REDs, K3 reads S_total
     if (ctx->s_prezeroed) SVA_CUDA_OK(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_zero, 0));
     else SVA_CUDA_OK(ctx, cudaMemsetAsync(ctx->S.p, 0, cells * sizeof(uint16_t), ctx->stream));
@@ -863,6 +918,7 @@ int sva_run_sgm(sva_ctx* ctx) {
         set_dirs(q, n == 8 ? all8 : all4, n);
         SVA_TRY(launch_dirs(ctx, q, nr, false));
     }
+    wall.stop();
     SVA_TRY(sva_run_wta(ctx, ctx->S.as<uint16_t>()));
     ctx->have_sgm = true; ctx->have_disp = true;
     return SVA_OK;

@@ -93,6 +93,9 @@ struct sva_ctx {
     bool has_mask = false;
     bool debug_store_full_s = false;
     int tune_sgm_split = 1;       // SVA_SGM_SPLIT: 8 paths as three launches (down-sweeping, up-sweeping, horizontal; default) or, 0, as one
+    int tune_sgm_hstore = 2;      // SVA_SGM_HSTORE: 1 = the first horizontal direction initialises S with plain stores (no memset) and the second accumulates;
+                                  // 2 (default) = and the second runs on the second stream next to the first row-sweeping group where the launches are not
+                                  // paced; 3 = always next to it; 0 = S zeroed by a memset next to K1, both horizontal directions in one launch
     int tune_sgm_pace = -1;       // SVA_SGM_PACE: keep all CTAs of a row-sweeping launch within pace_window rounds (of 9 rows) of each other.
                                   // -1 = automatic: on when one image row of C + S (W*D*4 bytes) is 768 KB or more.  The three directions of such a
                                   // launch share C and S lines in L2 only while their rows stay within the L2-resident window; unpaced drift is harmless

@@ -97,6 +97,7 @@ int sva_create(int device, sva_ctx** out) {
     c->stream = c->own_stream;
     if (const char* e = getenv("SVA_SGM_SPLIT")) c->tune_sgm_split = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
+    if (const char* e = getenv("SVA_SGM_HSTORE")) c->tune_sgm_hstore = atoi(e);
     if (const char* e = getenv("SVA_SGM_BULK")) c->tune_sgm_bulk = atoi(e);
     if (const char* e = getenv("SVA_PREZERO")) c->tune_prezero = atoi(e);
     if (const char* e = getenv("SVA_SGM_DIAG_SPLIT")) c->tune_sgm_diag_split = atoi(e);
