@@ -14,11 +14,13 @@
 // Diagonal paths use W lines of exactly H steps that wrap around the image edge and restart (L = C) where the predecessor
 // is outside the image, so every line of a launch has the same length.
 //
-// Schedule for 8 paths (sva_run_sgm): three launches — the three directions that sweep the rows downwards, the three that
-// sweep upwards, the two horizontal ones.  All lines of a row-sweeping launch advance one row per step, so a row's C and S
-// lines are touched by all three directions while they are L2-resident (DRAM sees C once and S once per launch); when an image
-// row of C + S is 768 KB or more the CTAs are additionally paced against the grid-wide minimum.  (Other groupings, several
-// lines per warp, a second stream and a last pass fused with K3 were measured and dropped: DESIGN.md §4.)
+// Schedule for 8 paths (sva_run_sgm): four launches — the horizontal direction -> first, WRITING S with plain stores (so S is never
+// zeroed), then <- accumulating with REDs like everything after it, then the three directions that sweep the rows downwards and the
+// three that sweep upwards.  All lines of a row-sweeping launch advance one row per step, so a row's C and S lines are touched by all
+// three directions while they are L2-resident (DRAM sees C once and S once per launch); when an image row of C + S is 768 KB or more
+// the CTAs are additionally paced against the grid-wide minimum.  The single-direction horizontal launches have only H warps: <- runs
+// on the second stream next to the first row-sweeping group where that group is not paced.  (Other groupings, several lines per warp
+// and a last pass fused with K3 were measured and dropped: DESIGN.md §4.)
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>

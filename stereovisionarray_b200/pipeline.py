@@ -1,6 +1,6 @@
 """Host-side driver of the volume-mode depth pipeline over the C ABI (one DepthContext per GPU).
 
-Stages: K1a AD volume -> K1b box/pack -> K2 SGM (three launches for 8 paths) -> K3 (WTA / LR / sub-pixel).
+Stages: K1a AD volume -> K1b box/pack -> K2 SGM (four launches for 8 paths: -> storing S, <-, the down-sweeping and the up-sweeping group) -> K3 (WTA / LR / sub-pixel).
 All compute happens in libsva_b200.so on the GPU; this module only marshals numpy buffers."""
 import ctypes as C
 
