@@ -150,6 +150,7 @@ static int prezero_s(sva_ctx* c) {
 }
 
 static int run_stage(sva_ctx* c, int stage) {
+    if (!c->in_stream_submit) c->ev_box_valid = false;  // work outside the capture stream uses AP too: the next streamed K1a waits for all of it
     NvtxRange range(stage == SVA_STAGE_AD ? "sva:K1a_ad_volume" : stage == SVA_STAGE_BOX ? "sva:K1b_box_cost" : stage == SVA_STAGE_SGM ? "sva:K2_sgm+K3_wta" : "sva:frame");
     switch (stage) {
         case SVA_STAGE_AD: {
@@ -470,8 +471,10 @@ int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, 
                        p->win_half != c->prm.win_half || p->min_disp != c->prm.min_disp || p->reserved[0] != c->prm.reserved[0])) {
         // a different geometry re-allocates workspaces: drain the pipeline first so no frame in flight still uses the old ones
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->h2d_stream));
+        if (c->ad_stream) SVA_CUDA_OK(c, cudaStreamSynchronize(c->ad_stream));
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->stream));
         SVA_CUDA_OK(c, cudaStreamSynchronize(c->d2h_stream));
+        c->ev_box_valid = false;
     }
     SVA_TRY(check_frame_args(c, p, ref, others, mask));  // a bad frame must not disturb the frames in flight: nothing is touched before this
     if (t >= 2) SVA_CUDA_OK(c, cudaEventSynchronize(c->ev_done[slot]));  // frame t-2 is out: its IoSet is free again
@@ -482,8 +485,40 @@ int sva_stream_submit(sva_ctx* c, const sva_params* p, const sva_image_u8* ref, 
     c->stream = compute;
     if (rc != SVA_OK) { swap_io(c); return rc; }  // (allocation failure): back onto the IoSet of frame t-1, the ticket is not consumed
     SVA_CUDA_OK(c, cudaEventRecord(c->ev_h2d[slot], c->h2d_stream));
-    SVA_CUDA_OK(c, cudaStreamWaitEvent(compute, c->ev_h2d[slot], 0));
-    SVA_TRY(run_stage(c, SVA_STAGE_ALL));
+    // (only where the SGM launches are not paced — c1-sized rows: next to paced launches the intruder costs more than it hides: c2 e2e 1.67 -> 1.76 ms)
+    if (c->tune_stream_ad_ahead && c->win_rows == 0 && (c->tune_stream_ad_ahead > 1 || (size_t)p->width * p->num_disp * 4 < 768 * 1024)) {
+        // K1a of this frame depends on nothing but its upload, and the AD volume is free as soon as the previous frame's K1b has read it: run
+        // it on a stream of its own, so that it executes NEXT TO the previous frame's first SGM launches (single horizontal directions: H warps
+        // bound by HBM latency, the SMs mostly idle) instead of after its K3.  K1b and everything after it stay in order on the compute stream.
+        if (!c->ad_stream) {
+            SVA_CUDA_OK(c, cudaStreamCreateWithFlags(&c->ad_stream, cudaStreamNonBlocking));
+            SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_ad, cudaEventDisableTiming));
+            SVA_CUDA_OK(c, cudaEventCreateWithFlags(&c->ev_box, cudaEventDisableTiming));
+            c->ev_box_valid = false;
+        }
+        SVA_CUDA_OK(c, cudaStreamWaitEvent(c->ad_stream, c->ev_h2d[slot], 0));
+        if (c->ev_box_valid) SVA_CUDA_OK(c, cudaStreamWaitEvent(c->ad_stream, c->ev_box, 0));
+        else {  // first frame of the stream (or after a drain): whatever the compute stream still does with AP comes first
+            SVA_CUDA_OK(c, cudaEventRecord(c->ev_box, compute));
+            SVA_CUDA_OK(c, cudaStreamWaitEvent(c->ad_stream, c->ev_box, 0));
+        }
+        c->in_stream_submit = true;
+        c->stream = c->ad_stream;
+        rc = run_stage(c, SVA_STAGE_AD);
+        c->stream = compute;
+        if (rc == SVA_OK) rc = cudaEventRecord(c->ev_ad, c->ad_stream) == cudaSuccess && cudaStreamWaitEvent(compute, c->ev_ad, 0) == cudaSuccess ? SVA_OK : SVA_ERR_CUDA;
+        if (rc == SVA_OK) rc = run_stage(c, SVA_STAGE_BOX);
+        if (rc == SVA_OK) {
+            rc = cudaEventRecord(c->ev_box, compute) == cudaSuccess ? SVA_OK : SVA_ERR_CUDA;
+            c->ev_box_valid = rc == SVA_OK;
+        }
+        if (rc == SVA_OK) rc = run_stage(c, SVA_STAGE_SGM);
+        c->in_stream_submit = false;
+        SVA_TRY(rc);
+    } else {
+        SVA_CUDA_OK(c, cudaStreamWaitEvent(compute, c->ev_h2d[slot], 0));
+        SVA_TRY(run_stage(c, SVA_STAGE_ALL));
+    }
     SVA_CUDA_OK(c, cudaEventRecord(c->ev_compute[slot], compute));
     SVA_CUDA_OK(c, cudaStreamWaitEvent(c->d2h_stream, c->ev_compute[slot], 0));
     const size_t px = (size_t)p->width * p->height;

@@ -77,6 +77,10 @@ struct sva_ctx {
     int tune_prezero = 1;      // SVA_PREZERO: overlap the S memset with K1a / K1b
     // ---- streaming pipeline (sva_stream_*) ----
     cudaStream_t h2d_stream = nullptr, d2h_stream = nullptr;
+    cudaStream_t ad_stream = nullptr;   // K1a of frame t + 1 next to the SGM of frame t (sva_stream_submit)
+    cudaEvent_t ev_ad = nullptr, ev_box = nullptr;
+    bool ev_box_valid = false, in_stream_submit = false;
+    int tune_stream_ad_ahead = 1;       // SVA_STREAM_AD_AHEAD
     cudaEvent_t ev_h2d[2] = {nullptr, nullptr}, ev_compute[2] = {nullptr, nullptr}, ev_done[2] = {nullptr, nullptr}, ev_mark = nullptr;
     IoSet alt;                 // the set not in use by the frame being submitted
     int64_t stream_ticket = 0; // next ticket

@@ -98,6 +98,7 @@ int sva_create(int device, sva_ctx** out) {
     if (const char* e = getenv("SVA_SGM_SPLIT")) c->tune_sgm_split = atoi(e);
     if (const char* e = getenv("SVA_SGM_PACE")) c->tune_sgm_pace = atoi(e);
     if (const char* e = getenv("SVA_SGM_HSTORE")) c->tune_sgm_hstore = atoi(e);
+    if (const char* e = getenv("SVA_STREAM_AD_AHEAD")) c->tune_stream_ad_ahead = atoi(e);
     if (const char* e = getenv("SVA_SGM_BULK")) c->tune_sgm_bulk = atoi(e);
     if (const char* e = getenv("SVA_PREZERO")) c->tune_prezero = atoi(e);
     if (const char* e = getenv("SVA_SGM_DIAG_SPLIT")) c->tune_sgm_diag_split = atoi(e);
@@ -123,6 +124,7 @@ int sva_destroy(sva_ctx* c) {
     if (c->tex) cudaDestroyTextureObject((cudaTextureObject_t)c->tex);
     if (c->aux_stream) cudaStreamSynchronize(c->aux_stream);
     if (c->h2d_stream) { cudaStreamSynchronize(c->h2d_stream); cudaStreamSynchronize(c->d2h_stream); }
+    if (c->ad_stream) cudaStreamSynchronize(c->ad_stream);
     std::vector<DevBuf*> bufs;
     c->device_bufs(bufs);
     for (DevBuf* b : bufs) c->release(*b);
@@ -134,6 +136,7 @@ int sva_destroy(sva_ctx* c) {
     for (cudaEvent_t e : c->event_pool) cudaEventDestroy(e);
     if (c->aux_stream) { cudaStreamDestroy(c->aux_stream); cudaEventDestroy(c->ev_fork); }
     if (c->ev_zero) cudaEventDestroy(c->ev_zero);
+    if (c->ad_stream) { cudaStreamDestroy(c->ad_stream); cudaEventDestroy(c->ev_ad); cudaEventDestroy(c->ev_box); }
     cudaStreamDestroy(c->own_stream);
     delete c;
     return SVA_OK;
