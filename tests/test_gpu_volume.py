@@ -31,6 +31,12 @@ CASES = [
     (150, 300, 24, [(1, 0), (0, -1), (-1, 1)], dict(win_half=9, n_paths=8, lr_gx=1, min_disp=2)),  # several row bands
     (90, 200, 16, [(3, 0), (-3, 1), (1, -4)], dict(win_half=3, n_paths=4, lr_gx=-1)),  # pair offsets beyond +-2: the line-image gather AD kernel
     (48, 260, 64, [(2, -2), (-2, 2), (0, 2), (2, 0)], dict(win_half=4, n_paths=8, lr_gx=1, min_disp=5)),  # |g| = 2 bodies of the image-space AD kernel, min_disp % 4 != 0
+    # the register form of the box filter (win_half % 8 == 4) beyond the configurations' 20: one lane, three lanes, seven lanes per window;
+    # several strips and row bands, ragged width, D % 16 != 0, the 3 x 3 and 4 x 4 pair-set kernels of K1a with tiles taller than one pass
+    (130, 530, 40, OFF8, dict(win_half=12, n_paths=8, lr_gx=-1, min_disp=1)),
+    (200, 300, 24, OFF15, dict(win_half=28, n_paths=4, lr_gx=1)),
+    (200, 280, 48, OFF8, dict(win_half=20, n_paths=8, lr_gx=-1)),
+    (97, 515, 72, [(-1, 0)], dict(win_half=4, n_paths=8, lr_gx=-1)),
 ]
 
 
