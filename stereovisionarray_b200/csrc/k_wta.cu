@@ -330,8 +330,10 @@ int sva_run_wta_rows(sva_ctx* ctx, const uint16_t* vol, int y0, int rows) {
         // register march + per-pixel finish (the default where D splits into 16 lanes x 4 / 8 / 12 / 16 cells)
         SVA_TRY(ctx->reserve(ctx->scratch2, (size_t)W * H * sizeof(uint16_t)));
         uint16_t* dwin = ctx->scratch2.as<uint16_t>();
-        int seg_len = ctx->tune_wta_seg;  // pixels per half-warp; a multiple of 16 keeps the unrolled rotation whole
-        seg_len = ((seg_len + 15) / 16) * 16;
+        // pixels per half-warp.  Short segments give more half-warps (the march is bound by the integer pipe and by latency) but pay a flush of
+        // the other view's diagonals per segment: measured best 80 - 96 up to c4's size (c1 0.086 -> 0.078 ms, c2 0.119 -> 0.096 ms), 160 at c3
+        int seg_len = ctx->tune_wta_seg > 0 ? ctx->tune_wta_seg : ((long long)H * div_up(W, 160) < 32768 ? 96 : 160);
+        seg_len = ((seg_len + 15) / 16) * 16;  // a multiple of 16 keeps the unrolled rotation whole
         const int segs = div_up(W, seg_len);
         {
             LaunchScope ls(ctx, "k_wta_seg");
