@@ -520,6 +520,23 @@ def run_c3(args, R, headline=False):
                 by_in_flight[in_flight] = R.max(ctxs[0].timer_stop()) / frames
                 for c in use:
                     c.rows_download()
+            # three frames in flight in the three-part form (sva_rows_run_part): part 0 of frame f, part 1 of frame f - 1, part 2 of frame f - 2 —
+            # every wait for a neighbour's state sits behind a later frame's cost volume, which needs no neighbour
+            if max_in_flight >= 3:
+                frames = 12
+                use = ctxs[:3]
+                R.barrier()
+                ctxs[0].timer_start()
+                for f in range(frames + 2):
+                    if f < frames:
+                        use[f % 3].rows_run_part(0)
+                    if 0 <= f - 1 < frames:
+                        use[(f - 1) % 3].rows_run_part(1)
+                    if f - 2 >= 0:
+                        use[(f - 2) % 3].rows_run_part(2)
+                by_in_flight["3 (three parts)"] = R.max(ctxs[0].timer_stop()) / frames
+                for c in use:
+                    c.rows_download()
             R.barrier()
             in_flight = min(by_in_flight, key=by_in_flight.get)
             thr = by_in_flight[in_flight]

@@ -288,6 +288,11 @@ int sva_rows_run(sva_ctx* ctx);
  * K3), for hosts that keep several frames in flight: several contexts share ONE stream (sva_get_stream / sva_set_stream) and the host
  * enqueues phase 0 of frame f, then phase 1 of frame f - P + 1 — frames overlap across GPUs without two big kernels ever running at once. */
 int sva_rows_run_phase(sva_ctx* ctx, int32_t phase);
+/* The same frame in three parts, for hosts with three or more frames in flight: part 0 = cost volume (+ horizontal paths on the ranks that do
+ * not start a sweep) — nothing in it waits for a neighbour; part 1 = the first sweep (+ horizontal paths on the two ranks that start one);
+ * part 2 = the other sweep and K3.  Enqueued as part 0 of frame f, part 1 of frame f - 1, part 2 of frame f - P + 1, every wait for a
+ * neighbour's state sits behind work of a later frame that needs no neighbour.  (sva_rows_run_phase: phase 0 = parts 0 + 1, phase 1 = part 2.) */
+int sva_rows_run_part(sva_ctx* ctx, int32_t part);
 int sva_rows_download(sva_ctx* ctx, uint16_t* out_disp_rows, float* out_subpix_rows);  /* the block's rows; out_subpix_rows may be NULL */
 int sva_rows_close(sva_ctx* ctx);
 /* one synchronous call per frame: upload + sva_rows_run + sva_rows_download */

@@ -24,7 +24,7 @@ EXPORTS = [
     "sva_frame_cost_device_ptr", "sva_frame_set_params", "sva_frame_sgm_directions", "sva_frame_wta_rows", "sva_frame_download_disparity_rows",
     "sva_frame_rows_begin", "sva_frame_sgm_rows",
     "sva_comm_get_unique_id", "sva_comm_init", "sva_comm_destroy", "sva_comm_barrier", "sva_frame_reduce_ad", "sva_depth_pair_sharded",
-    "sva_rows_open", "sva_rows_export", "sva_rows_connect", "sva_rows_connect_comm", "sva_rows_connect_local", "sva_rows_block", "sva_rows_run", "sva_rows_run_phase", "sva_get_stream",
+    "sva_rows_open", "sva_rows_export", "sva_rows_connect", "sva_rows_connect_comm", "sva_rows_connect_local", "sva_rows_block", "sva_rows_run", "sva_rows_run_phase", "sva_rows_run_part", "sva_get_stream",
     "sva_rows_download", "sva_rows_close", "sva_depth_rows_sharded",
 ]
 

@@ -75,7 +75,7 @@ struct RowsLink {
     uint8_t* next = nullptr;
     bool prev_ipc = false, next_ipc = false;
     uint32_t seq = 0;              // frames enqueued so far
-    int phase_done = 1;            // phases of frame `seq` enqueued so far (0: none yet, 1: both / first only — see sva_rows_run_phase)
+    int part_done = 2;             // last part of frame `seq` that was enqueued (2: the frame is complete — see sva_rows_run_part)
     long long timeout_ns = 20000LL * 1000000LL;
     uint32_t* flag(uint8_t* base, int i) const { return (uint32_t*)(base + (size_t)i * FLAG_STRIDE); }
     uint16_t* d_in(uint8_t* base) const { return (uint16_t*)(base + FLAGS_BYTES); }
@@ -333,6 +333,7 @@ int sva_rows_connect_local(sva_ctx* c, sva_ctx* prev, sva_ctx* next) {
 }
 
 int sva_rows_run_phase(sva_ctx* c, int32_t phase);
+int sva_rows_run_part(sva_ctx* c, int32_t part);
 
 int sva_rows_block(const sva_ctx* c, int32_t* out_y0, int32_t* out_rows) {
     if (!c || !c->rows_link || !out_y0 || !out_rows) return SVA_ERR_BAD_ARG;
@@ -346,17 +347,20 @@ int sva_rows_run(sva_ctx* c) {
     return sva_rows_run_phase(c, 1);
 }
 
-// One frame in two parts, so that a host with several contexts ON ONE STREAM can interleave frames without ever running two of the big
+// One frame in parts, so that a host with several contexts ON ONE STREAM can interleave frames without ever running two of the big
 // kernels at once (concurrent launches break the resident, paced waves of the SGM marches: measured 2.5x slower):
-//   phase 0 = cost volume of the block, horizontal paths, and the sweep that reaches this rank first;  phase 1 = the other sweep and K3.
-// Enqueue order for P frames in flight: phase 0 of frame f, then phase 1 of frame f - P + 1 — the wait for the far end of the second
-// sweep's chain is then spent computing the next frames' phase 0.
-int sva_rows_run_phase(sva_ctx* c, int32_t phase) {
+//   part 0 = cost volume of the block (+ the horizontal paths on the ranks that do not start a sweep): nothing in it waits for a neighbour;
+//   part 1 = the sweep that reaches this rank first (+ the horizontal paths on the two ranks that START a sweep, off the chain);
+//   part 2 = the other sweep and K3.
+// sva_rows_run_phase keeps the two-phase form (phase 0 = parts 0 + 1, phase 1 = part 2).  Enqueue order for P >= 3 frames in flight:
+// part 0 of frame f, part 1 of frame f - 1, part 2 of frame f - P + 1 — every wait for a neighbour's state then sits behind a part 0 of
+// a later frame, i.e. behind work that needs no neighbour.
+int sva_rows_run_part(sva_ctx* c, int32_t part) {
     if (!c) return SVA_ERR_BAD_ARG;
     RowsLink* l = (RowsLink*)c->rows_link;
     if (!l) return c->fail(SVA_ERR_STATE, "rows_run: sva_rows_open first");
-    if (phase != 0 && phase != 1) return c->fail(SVA_ERR_BAD_ARG, "rows_run_phase: phase must be 0 or 1");
-    if (phase == 0 ? l->phase_done != 1 : l->phase_done != 0) return c->fail(SVA_ERR_STATE, "rows_run_phase: phases of a frame run in order 0, 1");
+    if (part < 0 || part > 2) return c->fail(SVA_ERR_BAD_ARG, "rows_run_part: part must be 0, 1 or 2");
+    if (part != (l->part_done + 1) % 3) return c->fail(SVA_ERR_STATE, "rows_run_part: the parts of a frame run in order 0, 1, 2");
     if (!c->have_frame) return c->fail(SVA_ERR_STATE, "no frame uploaded");
     const sva_params& p = c->prm;
     if (p.width != l->W || p.height != l->H || p.num_disp != l->D || p.n_paths != 8) return c->fail(SVA_ERR_STATE, "rows_run: the uploaded frame does not match the geometry of sva_rows_open");
@@ -365,15 +369,10 @@ int sva_rows_run_phase(sva_ctx* c, int32_t phase) {
     SVA_CUDA_OK(c, cudaSetDevice(c->device));
     nvtxRangePushA("sva:rows_block");
     struct Pop { ~Pop() { nvtxRangePop(); } } pop;
-    const uint32_t seq = phase == 0 ? ++l->seq : l->seq;
-    l->phase_done = phase;
+    const uint32_t seq = part == 0 ? ++l->seq : l->seq;
+    l->part_done = part;
     const int y0 = l->y0, n = l->rows;
     uint32_t* err = l->flag(l->mem, F_ERR);
-    if (phase == 0) {
-        SVA_TRY(sva_frame_rows_begin(c, y0, n));
-        SVA_TRY(sva_frame_run(c, SVA_STAGE_AD));
-        SVA_TRY(sva_frame_run(c, SVA_STAGE_BOX));
-    }
     auto wait = [&](int f, uint32_t want) -> int {
         c->launches++;
         k_rows_wait<<<1, 1, 0, c->stream>>>(l->flag(l->mem, f), want, l->timeout_ns, err);
@@ -405,14 +404,30 @@ int sva_rows_run_phase(sva_ctx* c, int32_t phase) {
     // two ranks that START a sweep do so right after their cost volume and run their horizontal paths afterwards, off the chain.
     const bool starts_chain = G > 1 && (r == 0 || r == G - 1);
     const bool down_first = r < (G + 1) / 2;
-    if (phase == 0) {
+    if (part == 0) {
+        SVA_TRY(sva_frame_rows_begin(c, y0, n));
+        SVA_TRY(sva_frame_run(c, SVA_STAGE_AD));
+        SVA_TRY(sva_frame_run(c, SVA_STAGE_BOX));
         if (!starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
+        return SVA_OK;
+    }
+    if (part == 1) {
         SVA_TRY(sweep(down_first));
         if (starts_chain) SVA_TRY(sva_frame_sgm_rows(c, 2, y0, n, nullptr, nullptr));
         return SVA_OK;
     }
     SVA_TRY(sweep(!down_first));
     return sva_frame_wta_rows(c, nullptr, y0, n);
+}
+
+int sva_rows_run_phase(sva_ctx* c, int32_t phase) {
+    if (!c) return SVA_ERR_BAD_ARG;
+    if (phase != 0 && phase != 1) return c->fail(SVA_ERR_BAD_ARG, "rows_run_phase: phase must be 0 or 1");
+    if (phase == 0) {
+        SVA_TRY(sva_rows_run_part(c, 0));
+        return sva_rows_run_part(c, 1);
+    }
+    return sva_rows_run_part(c, 2);
 }
 
 int sva_rows_download(sva_ctx* c, uint16_t* out_disp_rows, float* out_subpix_rows) {

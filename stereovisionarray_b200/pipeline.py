@@ -245,6 +245,10 @@ class DepthContext:
         """enqueue this rank's block of the uploaded frame (asynchronous)"""
         check(self._h, self._L.sva_rows_run(self._h))
 
+    def rows_run_part(self, part):
+        """part 0: cost volume (+ horizontal paths off the chain's ends); part 1: first sweep; part 2: second sweep + K3 (see sva_rows_run_part)"""
+        check(self._h, self._L.sva_rows_run_part(self._h, int(part)))
+
     def rows_run_phase(self, phase):
         """phase 0: cost volume, horizontal paths, first sweep; phase 1: second sweep + K3 (see sva_rows_run_phase)"""
         check(self._h, self._L.sva_rows_run_phase(self._h, int(phase)))

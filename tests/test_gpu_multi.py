@@ -119,11 +119,13 @@ def test_two_gpus_every_scheme_against_the_oracle():
     assert len(lines) >= 9 and all("bit-exact" in l for l in lines), r.stdout
 
 
-def test_rows_direct_frames_in_flight_on_one_stream(oracle):
-    """several frames in flight without concurrent kernels: every rank has P = 2 contexts (own links, own volumes) on ONE stream, and the host
-    enqueues phase 0 of frame f before phase 1 of frame f - 1 (sva_rows_run_phase).  G = 3 local ranks, four frames through the pipeline."""
+@pytest.mark.parametrize("P", [2, 3])
+def test_rows_direct_frames_in_flight_on_one_stream(oracle, P):
+    """several frames in flight without concurrent kernels: every rank has P contexts (own links, own volumes) on ONE stream.  P = 2: the host
+    enqueues phase 0 of frame f before phase 1 of frame f - 1 (sva_rows_run_phase); P = 3: the three-part form (sva_rows_run_part) — part 0 of
+    frame f, part 1 of frame f - 1, part 2 of frame f - 2.  G = 3 local ranks, five frames through the pipeline."""
     from stereovisionarray_b200.pipeline import DepthContext
-    h, w, D, G, P = 70, 120, 64, 3, 2
+    h, w, D, G = 70, 120, 64, 3
     inputs = [synth.make_scene(h, w, D, OFF8, 1700 + i, face=(i == 1)) for i in range(P)]
     p = abi.make_params(w, h, D, OFF8, win_half=4, n_paths=8, lr_gx=-1)
     ctxs = [[DepthContext(0) for _ in range(P)] for _ in range(G)]
@@ -141,13 +143,21 @@ def test_rows_direct_frames_in_flight_on_one_stream(oracle):
             for c in ctxs[r]:
                 y0, n = c.rows_block()
                 c.rows_begin(y0, n); c.run(abi.STAGE_AD); c.run(abi.STAGE_BOX); c.sgm_rows(2, y0, n); c.wta_rows(None, y0, n); c.synchronize()
-        frames = 4
+        frames = 5
         for f in range(frames + P - 1):
             for r in range(G):
-                if f < frames:
-                    ctxs[r][f % P].rows_run_phase(0)
-                if f - P + 1 >= 0:
-                    ctxs[r][(f - P + 1) % P].rows_run_phase(1)
+                if P == 2:
+                    if f < frames:
+                        ctxs[r][f % P].rows_run_phase(0)
+                    if f - P + 1 >= 0:
+                        ctxs[r][(f - P + 1) % P].rows_run_phase(1)
+                else:
+                    if f < frames:
+                        ctxs[r][f % P].rows_run_part(0)
+                    if 0 <= f - 1 < frames:
+                        ctxs[r][(f - 1) % P].rows_run_part(1)
+                    if f - 2 >= 0:
+                        ctxs[r][(f - 2) % P].rows_run_part(2)
         for j in range(P):
             parts = [ctxs[r][j].rows_download() for r in range(G)]
             disp = np.concatenate([d for d, _ in parts]); sub = np.concatenate([s for _, s in parts])
