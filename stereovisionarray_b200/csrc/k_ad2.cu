@@ -12,13 +12,18 @@
 // The four byte differences go into two accumulators WITHOUT being split first: X += ad (a plain 32-bit add, the bytes bleed into
 // each other on purpose) and Y += (pixels 1 and 3 as u16x2, one PRMT); because X = E + 256 * Y (mod 2^32) with E = (pixels 0 and 2
 // as u16x2), the even pixels are recovered once per tile row as X - (Y << 8).  Per source word that is VABSDIFF4 + PRMT on the
-// integer ALU pipe (the bound: 2 warp-instructions / clk / SM) and two adds that the compiler places on the FMA pipe.
+// integer ALU pipe (the bound: 2 warp-instructions / clk / SM) and two adds — written as IMADs with a run-time 1 in the kernels compiled
+// per pair set, so that they stay on the FMA pipe (left to itself ptxas folds them into 3-input IADD3s on the integer pipe).
 //
 // A CTA = TH rows x 128 columns x 32 disparities, TH = 8 * R.  The views live in HBM as zero-bordered, 16-byte-pitched copies
 // (out-of-image source = 0 = the spec's OOB value, so there are no bounds checks); the part of every view that the tile's disparity
 // range can touch (TH + 31 * |gy| rows) is staged once per CTA with 16-byte cp.async row copies, and the 512 threads then walk the
-// tile 8 rows at a time.  Tall tiles amortise the halo rows and the per-CTA set-up; the host picks TH so that the grid fills whole
-// waves (sva_run_ad2).
+// tile 8 rows at a time.  Tall tiles amortise the halo rows and the per-CTA set-up; the host picks TH (24 - 32 rows while the grid
+// keeps five waves of the 2 CTAs per SM: sva_run_ad2).
+//
+// Three kernels: k_ad_tile_set<SET> (the pair set known at compile time: straight-line code, no dispatch — the 3 x 3 array, the
+// rectified pair and, with 16 disparities per CTA, the 4 x 4 array), k_ad_tile<false> (any pair set that fits one staging group:
+// a 25-way dispatch per pair) and k_ad_tile<true> (several staging groups, 8-row tiles, the accumulators live across the groups).
 #include <algorithm>
 #include <cstdlib>
 

@@ -397,6 +397,9 @@ k_box_planar(BoxPParams q) {
 // difference stays within +-32767.  Per row and 8 columns x 2 cells: 14 + 4M shuffles instead of 8 STS.64 + 16 LDS.64 + 10 shuffles.
 // Warm-up rows (the 2K - 1 rows before a band's first output) have nothing leaving, so they are summed as packed words first —
 // `chunk` rows at a time, as many as keep a field below 32768 — and only every chunk goes through the horizontal pass.
+// A lane's 32 bytes of a row arrive in ONE 256-bit load (LDG.E.256: 1 KB of whole sectors per warp-instruction; two 128-bit loads per lane
+// touch every sector twice).  PF = rows the loads run ahead of the arithmetic (1; 2 measured no faster), OCC = CTAs per SM the kernel is
+// compiled for (2: up to 128 registers; 3: 80 registers, no spills — chosen per launch by sva_launch_box_planar's cost model).
 template <int K, int PF, int OCC>
 __global__ void __launch_bounds__(256, OCC)
 k_box_planar_shfl(BoxPParams q) {
