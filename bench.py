@@ -538,6 +538,46 @@ def run_c3(args, R, headline=False):
                 for c in use:
                     c.rows_download()
             R.barrier()
+            # The sweeps as a software pipeline ACROSS the ranks.  In the orders above every rank enqueues "its sweep of frame f" at the same point
+            # of the same iteration, so the hand-off still ripples rank by rank inside one iteration and each rank idles while it does.  Skewed
+            # by chain position, iteration i of rank r runs the cost volume of frame i, its FIRST sweep of frame i - 1 - min(pd, pu) and its second
+            # sweep + K3 of frame i - 1 - max(pd, pu) (pd = r, pu = G - 1 - r: hops from the start of the down / up chain): the state a sweep needs
+            # was produced by the neighbour ONE ITERATION EARLIER, so no wait ever blocks.  Needs G + 1 contexts per GPU (frames in flight);
+            # reported as the steady-state slope between a 16- and a 48-frame run and as the 48-frame average (fill and drain included).
+            skew = None
+            try:
+                G = world
+                P = G + 1
+                while len(ctxs) < P:
+                    c = DepthContext(R.local_rank)
+                    ctxs.append(c)
+                    c.set_stream(ctxs[0].get_stream())
+                    c.upload(p, sc["ref"], sc["others"], sc["mask"])
+                    sdist.rows_direct_connect(c, p, rank, world)
+                    c.rows_run()
+                    c.rows_download()
+                pd, pu = rank, G - 1 - rank
+                lag1, lag2 = 1 + min(pd, pu), 1 + max(pd, pu)
+                t_run = {}
+                for frames in (16, 48):
+                    R.barrier()
+                    ctxs[0].timer_start()
+                    for i in range(frames + G):
+                        if i < frames:
+                            ctxs[i % P].rows_run_part(0)
+                        if 0 <= i - lag1 < frames:
+                            ctxs[(i - lag1) % P].rows_run_part(1)
+                        if 0 <= i - lag2 < frames:
+                            ctxs[(i - lag2) % P].rows_run_part(2)
+                    t_run[frames] = R.max(ctxs[0].timer_stop())
+                    for c in ctxs:
+                        c.rows_download()
+                skew = {"contexts_per_gpu": P, "ms_per_frame_steady_state": round((t_run[48] - t_run[16]) / 32, 3), "ms_per_frame_48_frames": round(t_run[48] / 48, 3),
+                        "order": "iteration i of rank r: part 0 of frame i, part 1 of frame i - 1 - min(r, G-1-r), part 2 of frame i - 1 - max(r, G-1-r) (sva_rows_run_part)"}
+                by_in_flight["%d (skewed by chain position, 48 frames incl. fill and drain)" % P] = t_run[48] / 48
+            except Exception as e:  # noqa: BLE001 — the figures above stand on their own
+                skew = {"error": "%s: %s" % (type(e).__name__, str(e)[:200])}
+            R.barrier()
             in_flight = min(by_in_flight, key=by_in_flight.get)
             thr = by_in_flight[in_flight]
         finally:
@@ -548,7 +588,7 @@ def run_c3(args, R, headline=False):
                                 "%.1f MB of path state straight into the next GPU's memory (CUDA IPC over NVLink), sequenced by device flags; no volume collective, no NCCL on the data path"
                                 % (blocks, 3 * p.width * p.num_disp * 2 / 1e6),
                    latency_ms=round(lat, 3), latency_value=round(mde / (lat / 1e3), 1), in_flight=in_flight, ms_per_frame=round(thr, 3), frames_per_s=round(1e3 / thr, 2),
-                   ms_per_frame_by_in_flight={str(k): round(v, 3) for k, v in by_in_flight.items()},
+                   ms_per_frame_by_in_flight={str(k): round(v, 3) for k, v in by_in_flight.items()}, skewed_pipeline=skew,
                    value=round(mde / (thr / 1e3), 1), parity="tools/check_sharded.py --c3: bit-exact against the oracle digests (profiles/)")
     if not headline:
         return res

@@ -119,11 +119,13 @@ def test_two_gpus_every_scheme_against_the_oracle():
     assert len(lines) >= 9 and all("bit-exact" in l for l in lines), r.stdout
 
 
-@pytest.mark.parametrize("P", [2, 3])
+@pytest.mark.parametrize("P", [2, 3, 4])
 def test_rows_direct_frames_in_flight_on_one_stream(oracle, P):
     """several frames in flight without concurrent kernels: every rank has P contexts (own links, own volumes) on ONE stream.  P = 2: the host
     enqueues phase 0 of frame f before phase 1 of frame f - 1 (sva_rows_run_phase); P = 3: the three-part form (sva_rows_run_part) — part 0 of
-    frame f, part 1 of frame f - 1, part 2 of frame f - 2.  G = 3 local ranks, five frames through the pipeline."""
+    frame f, part 1 of frame f - 1, part 2 of frame f - 2; P = 4 = G + 1: the order skewed by chain position (iteration i of rank r: part 0 of
+    frame i, part 1 of frame i - 1 - min(r, G-1-r), part 2 of frame i - 1 - max(r, G-1-r)) — every state a sweep needs was produced by the
+    neighbour one iteration earlier.  G = 3 local ranks, five (P = 4: nine) frames through the pipeline."""
     from stereovisionarray_b200.pipeline import DepthContext
     h, w, D, G = 70, 120, 64, 3
     inputs = [synth.make_scene(h, w, D, OFF8, 1700 + i, face=(i == 1)) for i in range(P)]
@@ -143,10 +145,18 @@ def test_rows_direct_frames_in_flight_on_one_stream(oracle, P):
             for c in ctxs[r]:
                 y0, n = c.rows_block()
                 c.rows_begin(y0, n); c.run(abi.STAGE_AD); c.run(abi.STAGE_BOX); c.sgm_rows(2, y0, n); c.wta_rows(None, y0, n); c.synchronize()
-        frames = 5
+        frames = 9 if P == 4 else 5
         for f in range(frames + P - 1):
             for r in range(G):
-                if P == 2:
+                if P == 4:
+                    lag1, lag2 = 1 + min(r, G - 1 - r), 1 + max(r, G - 1 - r)
+                    if f < frames:
+                        ctxs[r][f % P].rows_run_part(0)
+                    if 0 <= f - lag1 < frames:
+                        ctxs[r][(f - lag1) % P].rows_run_part(1)
+                    if 0 <= f - lag2 < frames:
+                        ctxs[r][(f - lag2) % P].rows_run_part(2)
+                elif P == 2:
                     if f < frames:
                         ctxs[r][f % P].rows_run_phase(0)
                     if f - P + 1 >= 0:
