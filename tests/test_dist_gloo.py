@@ -279,3 +279,30 @@ def test_row_block_pipeline_with_the_oracle_recurrence(world):
         p.join(180)
         assert p.exitcode == 0
     assert q.get(timeout=10)
+
+
+def test_rows_skewed_order_is_a_software_pipeline_across_the_ranks():
+    """the enqueue order of dist.rows_skewed_order (no GPU): every frame's parts run in order on every rank, a sweep runs on a rank exactly one
+    iteration after it ran on the rank it comes from, and a context (frame f % (world + 1)) is never reused before its frame is complete"""
+    for world in range(1, 9):
+        frames = 3 * world + 2
+        P = world + 1
+        orders = [sdist.rows_skewed_order(r, world, frames) for r in range(world)]
+        when = [{} for _ in range(world)]  # (part, frame) -> (iteration, position inside it)
+        for r in range(world):
+            assert len(orders[r]) == frames + world
+            for i, step in enumerate(orders[r]):
+                for k, item in enumerate(step):
+                    assert item not in when[r], "enqueued twice"
+                    when[r][item] = (i, k)
+            for f in range(frames):
+                assert when[r][(0, f)] < when[r][(1, f)] < when[r][(2, f)], "parts of a frame in order"
+                if f + P < frames:  # the context is free again before its next frame starts
+                    assert when[r][(2, f)] < when[r][(0, f + P)]
+        down_first = lambda r: r < (world + 1) // 2  # csrc/sva_dist.cu: the sweep that reaches the rank first is its part 1
+        down = lambda r, f: when[r][(1 if down_first(r) else 2, f)][0]
+        up = lambda r, f: when[r][(2 if down_first(r) else 1, f)][0]
+        for f in range(frames):
+            for r in range(1, world):
+                assert down(r, f) == down(r - 1, f) + 1, "the down sweep moves one rank per iteration"
+                assert up(r - 1, f) == up(r, f) + 1, "the up sweep moves one rank per iteration"
